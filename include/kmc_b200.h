@@ -1,0 +1,185 @@
+/* kmc_b200.h — C ABI of the B200-native LiDAR deskew (motion compensation) path.
+ *
+ * This is the drop-in boundary for ONE path of fracgawd/kitti_motion_compensation: the per-point deskew
+ *   kmc::MotionCompensateFrame        include/kitti_motion_compensation/motion_compensation.hpp:13
+ *   kmc::MotionCompensatePoint        include/kitti_motion_compensation/motion_compensation.hpp:10-11
+ *   TrajectoryInterpolator            include/kitti_motion_compensation/trajectory_interpolation.hpp:11-31
+ *   kmc::lie::{Exp,Log,...}           include/kitti_motion_compensation/lie_algebra.hpp:12-26
+ *   kmc::GetPseudoTimeStamps          include/kitti_motion_compensation/timestamp_mocking.hpp:7-11
+ * (citations are relative to the reference repository root).  The reference has no FFI of its own — its boundary is
+ * a C++ shared library with Eigen types in the signatures — so this header is what a binding of that path would
+ * bind: plain pointers, sizes and doubles, no C++/Eigen/torch types.  The headers under include/kitti_motion_compensation/ hold
+ * the C++ mirror of the reference API implemented on top of these entry points.
+ *
+ * Conventions
+ *   - A scan is the KITTI on-disk format (reference data_io.hpp:24-33): n points x 4 float32, "x y z i" interleaved,
+ *     16 bytes per point.  Device pointers must be 16-byte aligned.
+ *   - Poses are 4x4 doubles, COLUMN-major, i.e. exactly Eigen::Affine3d::matrix().data().
+ *   - Times are doubles in seconds (kmc::Time, data_types.hpp:20).
+ *   - Every function returns a kmc_b200_status (0 == KMC_B200_OK).  Nothing here aborts or throws; the C++ mirror
+ *     re-creates the reference's assert-abort behaviour on top (trajectory_interpolation.cpp:9,32).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device entry points are
+ *     asynchronous with respect to the host; *_host entry points return after the result is in the caller's memory.
+ *   - There is NO CPU fallback: without a usable CUDA device the compute entry points return
+ *     KMC_B200_ERR_CUDA / KMC_B200_ERR_NO_DEVICE.
+ */
+#ifndef KMC_B200_H_
+#define KMC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMC_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define KMC_B200_API __attribute__((visibility("default")))
+#else
+#define KMC_B200_API
+#endif
+
+typedef enum kmc_b200_status {
+  KMC_B200_OK = 0,
+  KMC_B200_ERR_NULL_POINTER = -1,
+  KMC_B200_ERR_BAD_SIZE = -2,           /* negative n, n_frames, offsets not non-decreasing, misaligned pointer */
+  KMC_B200_ERR_TIME_OUT_OF_RANGE = -3,  /* requested/point time outside [t_start, t_end]: the reference asserts here */
+  KMC_B200_ERR_EMPTY_INTERVAL = -4,     /* t_end <= t_start (the reference divides by zero, :49-51) */
+  KMC_B200_ERR_NOT_RIGID = -5,          /* pose with non-finite entries or det(linear) <= 0 */
+  KMC_B200_ERR_CUDA = -6,               /* a CUDA runtime call failed; text in kmc_b200_last_error() */
+  KMC_B200_ERR_NO_DEVICE = -7,
+  KMC_B200_ERR_BAD_MODE = -8,
+  KMC_B200_ERR_CAPACITY = -9,           /* scan larger than the handle's capacity */
+  KMC_B200_ERR_IO = -10                 /* file could not be opened / is not a multiple of 16 bytes */
+} kmc_b200_status;
+
+/* Where a point's position on the trajectory comes from. */
+typedef enum kmc_b200_time_mode {
+  /* w holds the intensity and passes through bit-exactly.  The fraction of the scan completed is computed in the
+   * kernel from the azimuth: (pi - atan2(y, x)) / 2pi  (timestamp_mocking.cpp:46) — the fusion of
+   * GetPseudoTimeStamps into the deskew kernel.  32 B/point of traffic, no per-point stamps in memory. */
+  KMC_B200_TIME_FROM_AZIMUTH = 0,
+  /* w holds the point's fraction of the trajectory x_i = (t_i - t_start)/(t_end - t_start) in [0, 1]
+   * (trajectory_interpolation.cpp:49-51) and passes through unchanged.  Used by the C++ mirror of
+   * MotionCompensateFrame, which must honour whatever LidarScan::timestamps holds (data_types.hpp:58). */
+  KMC_B200_TIME_FROM_W = 1
+} kmc_b200_time_mode;
+
+/* Per-frame constants of the fused kernel: 64 bytes, computed once per frame on the host in double and rounded to
+ * float.  With xi = [rho; phi] = Log(T_start^-1 T_end), theta = |phi|, a = phi/theta (0 if theta == 0):
+ *   phi[3], theta2 = theta^2
+ *   rho_perp[3] = rho - a (a.rho),  c0 = 0.5 - x_req          (FROM_AZIMUTH: s = c0 - atan2(y,x)/2pi)
+ *   rho_par[3]  = a (a.rho),        x_req = (t_req - t_start)/(t_end - t_start)   (FROM_W: s = w - x_req)
+ *   phi_x_rho[3] = phi x rho,       wide = 1 when theta^2 > KMC_B200_SERIES_THETA2_MAX (kernel then uses the
+ *                                   half-angle polynomials valid up to theta = pi), else 0
+ * The correction applied to a point p captured at trajectory fraction x is  Exp((x - x_req) xi) p. */
+typedef struct kmc_b200_frame_params {
+  float phi[3];
+  float theta2;
+  float rho_perp[3];
+  float c0;
+  float rho_par[3];
+  float x_req;
+  float phi_x_rho[3];
+  float wide;
+} kmc_b200_frame_params;
+
+/* Largest theta^2 (rad^2 per scan) handled by the short in-kernel power series. */
+#define KMC_B200_SERIES_THETA2_MAX 1.0f
+
+typedef struct kmc_b200_handle kmc_b200_handle; /* opaque: device + stream + pinned/device staging (the "DataHandle") */
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+KMC_B200_API int kmc_b200_version(void);
+KMC_B200_API const char* kmc_b200_status_string(int status);
+/* Text of the last error raised on the calling thread (CUDA error strings included); never NULL. */
+KMC_B200_API const char* kmc_b200_last_error(void);
+/* Number of CUDA devices visible, or a negative status. */
+KMC_B200_API int kmc_b200_device_count(void);
+/* Kernels this library has launched in the calling process so far (every compute entry point ends in one). */
+KMC_B200_API uint64_t kmc_b200_launch_count(void);
+
+/* ---- host, double precision: the once-per-frame part of the path ----------------------------------------------
+ * Replaces, per frame, what the reference recomputes for every point: Log(P1^-1 P2) incl. the polar projection of
+ * T.rotation() (trajectory_interpolation.cpp:35, lie_algebra.cpp:94-103). */
+KMC_B200_API int kmc_b200_frame_params_from_poses(const double T_start_colmajor[16], const double T_end_colmajor[16],
+                                     double t_start, double t_end, double t_req, kmc_b200_frame_params* out);
+/* Same from an explicit twist xi = [rho; phi] of the whole scan and the requested fraction x_req in [0,1]. */
+KMC_B200_API int kmc_b200_frame_params_from_twist(const double xi[6], double x_req, kmc_b200_frame_params* out);
+
+/* Lie algebra on the host (lie_algebra.hpp:12-26); 3x3 / 4x4 matrices column-major. */
+KMC_B200_API int kmc_b200_so3_hat(const double phi[3], double out3x3[9]);
+KMC_B200_API int kmc_b200_so3_vee(const double m3x3[9], double out[3]);
+KMC_B200_API int kmc_b200_so3_exp(const double phi[3], double out3x3[9]);
+KMC_B200_API int kmc_b200_so3_log(const double R3x3[9], double out[3]);
+KMC_B200_API int kmc_b200_so3_left_jacobian(const double phi[3], double out3x3[9]);
+KMC_B200_API int kmc_b200_so3_inverse_left_jacobian(const double phi[3], double out3x3[9]);
+KMC_B200_API int kmc_b200_se3_exp(const double xi[6], double T_colmajor[16]);
+KMC_B200_API int kmc_b200_se3_log(const double T_colmajor[16], double xi[6]);
+/* TrajectoryInterpolator::GetPoseAtTime / RelativePoseBetweenTimes (trajectory_interpolation.hpp:17-19).
+ * KMC_B200_ERR_TIME_OUT_OF_RANGE where the reference would abort. */
+KMC_B200_API int kmc_b200_pose_at_time(double t1, const double P1[16], double t2, const double P2[16], double t, double out[16]);
+KMC_B200_API int kmc_b200_relative_pose_between_times(double t1, const double P1[16], double t2, const double P2[16],
+                                         double anchor_time, double query_time, double out[16]);
+/* FractionOfScanCompleted / GetPseudoTimeStamp for one point (timestamp_mocking.hpp:7-9). */
+KMC_B200_API double kmc_b200_fraction_of_scan_completed(double x, double y);
+KMC_B200_API double kmc_b200_pseudo_time_stamp(double x, double y, double scan_start, double scan_end);
+
+/* Contiguous split of n_items over n_parts (frame sharding across GPUs): part `index` owns [*begin, *end). */
+KMC_B200_API int kmc_b200_shard_range(int64_t n_items, int32_t n_parts, int32_t index, int64_t* begin, int64_t* end);
+
+/* ---- device entry points (pointers are DEVICE pointers on the current device) ---------------------------------- */
+/* One frame.  Per-frame constants travel as a __grid_constant__ kernel parameter (constant bank).  in == out is
+ * allowed (each thread reads then writes its own point). */
+KMC_B200_API int kmc_b200_deskew_frame_device(const float* xyzi_in, float* xyzi_out, int64_t n_points,
+                                 const kmc_b200_frame_params* params_host, int time_mode, void* stream);
+/* A batch of n_frames frames stored back to back.  frame_offsets_dev has n_frames+1 non-decreasing int64 entries
+ * (points, not bytes), frame_offsets[0] == 0 and frame_offsets[n_frames] == n_points_total; params_dev has n_frames
+ * records.  Both tables live in device memory. */
+KMC_B200_API int kmc_b200_deskew_batch_device(const float* xyzi_in, float* xyzi_out, const int64_t* frame_offsets_dev,
+                                 const kmc_b200_frame_params* params_dev, int32_t n_frames, int64_t n_points_total,
+                                 int time_mode, void* stream);
+/* GetPseudoTimeStamps (timestamp_mocking.cpp:56-63) on the device, double precision: stamps[i] =
+ * start + frac(x_i, y_i) * (end - start). */
+KMC_B200_API int kmc_b200_pseudo_time_stamps_device(const float* xyzi_in, double* stamps_out, int64_t n_points, double scan_start,
+                                       double scan_end, void* stream);
+/* Seeded synthetic HDL-64E style scans written straight into device memory (benchmark input):
+ * n_scans scans of points_per_scan points, scan k uses seed + first_scan_index + k, so a scan's content does not
+ * depend on which GPU generates it.  n_rings x azimuth steps, ring-major, log-uniform range in [2, 120) m. */
+KMC_B200_API int kmc_b200_synth_scans_device(float* xyzi_out, int64_t points_per_scan, int32_t n_scans, int32_t n_rings,
+                                uint64_t seed, int64_t first_scan_index, void* stream);
+/* Per-frame constants for synthetic frame `first_scan_index + k` (host, double -> float), the twist drawn from the
+ * distribution in SURVEY 8d config 2.  xi_out (optional, 6 doubles per frame) receives the twist. */
+KMC_B200_API int kmc_b200_synth_frame_params(int32_t n_frames, uint64_t seed, int64_t first_scan_index, double x_req,
+                                kmc_b200_frame_params* params_out_host, double* xi_out);
+
+/* ---- handle: device + stream + staging buffers (the KittiPclLoader-style owner, data_io.hpp:19-83) -------------- */
+/* capacity_points: largest single transfer chunk the handle can stage (reference loader: 250 000, data_io.hpp:17). */
+KMC_B200_API int kmc_b200_handle_create(int device, int64_t capacity_points, kmc_b200_handle** out);
+KMC_B200_API int kmc_b200_handle_destroy(kmc_b200_handle* h);
+KMC_B200_API int kmc_b200_handle_device(const kmc_b200_handle* h);
+KMC_B200_API int64_t kmc_b200_handle_capacity(const kmc_b200_handle* h);
+
+/* ---- host entry points: HOST pointers, H2D + kernel + D2H inside the call ---------------------------------------- */
+/* One frame (any n_points; processed in capacity-sized chunks, copies and kernels overlapped on the handle's
+ * streams).  Pageable or pinned host memory. */
+KMC_B200_API int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* xyzi_in, float* xyzi_out, int64_t n_points,
+                               const kmc_b200_frame_params* params, int time_mode);
+/* A batch of frames stored back to back in host memory; frame_offsets/params are HOST tables (n_frames+1 / n_frames). */
+KMC_B200_API int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* xyzi_in, float* xyzi_out, const int64_t* frame_offsets,
+                               const kmc_b200_frame_params* params, int32_t n_frames, int time_mode);
+/* The same batch split into contiguous frame ranges over several devices, one host thread + handle per device, no
+ * collective (frames are independent).  handles[i] must live on distinct devices. */
+KMC_B200_API int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_handles, const float* xyzi_in,
+                                    float* xyzi_out, const int64_t* frame_offsets, const kmc_b200_frame_params* params,
+                                    int32_t n_frames, int time_mode);
+/* KITTI .bin in, deskewed .bin out (KittiPclLoader::LoadPointcloud + MotionCompensateFrame + WritePointcloud,
+ * data_io.cpp:101-138, 287-313) without the float->double->float round trip.  n_points_out may be NULL. */
+KMC_B200_API int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out,
+                             const kmc_b200_frame_params* params, int64_t* n_points_out);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* KMC_B200_H_ */

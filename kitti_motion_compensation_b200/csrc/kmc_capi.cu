@@ -1,0 +1,531 @@
+// kmc_capi.cu — the C ABI declared in include/kmc_b200.h: argument checking, per-frame host prep, stream/handle
+// management, host<->device pipelines, multi-GPU frame sharding.  No CPU fallback lives here: every compute entry point
+// ends in a kernel launch from kmc_kernels.cu or an error status.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kmc_b200.h"
+#include "kmc_host_math.hpp"
+#include "kmc_kernels.cuh"
+
+namespace {
+
+thread_local std::string t_last_error;
+
+int Fail(int status, const std::string& what) {
+  t_last_error = what;
+  return status;
+}
+
+int FailCuda(cudaError_t e, const char* where) {
+  t_last_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? KMC_B200_ERR_NO_DEVICE : KMC_B200_ERR_CUDA;
+}
+
+#define KMC_CUDA_TRY(expr)                                  \
+  do {                                                      \
+    cudaError_t const e_ = (expr);                          \
+    if (e_ != cudaSuccess) return FailCuda(e_, #expr);      \
+  } while (0)
+
+constexpr int kMaxDevices = 64;
+int g_sm_count[kMaxDevices];
+std::once_flag g_sm_once[kMaxDevices];
+
+int SmCount(int device, int* out) {
+  if (device < 0 || device >= kMaxDevices) return Fail(KMC_B200_ERR_NO_DEVICE, "device ordinal out of range");
+  cudaError_t err = cudaSuccess;
+  std::call_once(g_sm_once[device], [&] {
+    int v = 0;
+    err = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    g_sm_count[device] = (err == cudaSuccess) ? v : 0;
+  });
+  if (err != cudaSuccess) return FailCuda(err, "cudaDeviceGetAttribute(MultiProcessorCount)");
+  if (g_sm_count[device] <= 0) return Fail(KMC_B200_ERR_NO_DEVICE, "device reports no multiprocessors");
+  *out = g_sm_count[device];
+  return KMC_B200_OK;
+}
+
+bool ValidMode(int mode) { return mode == KMC_B200_TIME_FROM_AZIMUTH || mode == KMC_B200_TIME_FROM_W; }
+bool Aligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+bool IsPinnedHost(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();  // clear
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+
+uint64_t Mix(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+double Uniform01(uint64_t& state) {
+  state = Mix(state);
+  return static_cast<double>(state >> 11) * (1.0 / 9007199254740992.0);
+}
+double Normal(uint64_t& state) {
+  double u1 = Uniform01(state), u2 = Uniform01(state);
+  if (u1 < 1e-300) u1 = 1e-300;
+  return std::sqrt(-2.0 * std::log(u1)) * std::cos(2.0 * M_PI * u2);
+}
+
+}  // namespace
+
+// =============================================================================================================
+// handle
+// =============================================================================================================
+struct kmc_b200_handle {
+  static constexpr int kSlots = 3;
+  int device = -1;
+  int sm_count = 0;
+  int64_t capacity = 0;  // points per staging slot
+  cudaStream_t stream[kSlots] = {};
+  cudaEvent_t done[kSlots] = {};
+  float* d_in[kSlots] = {};
+  float* d_out[kSlots] = {};
+  float* h_in[kSlots] = {};   // pinned
+  float* h_out[kSlots] = {};  // pinned
+  // device copies of the batch tables
+  int64_t* d_offsets = nullptr;
+  kmc_b200_frame_params* d_params = nullptr;
+  int64_t table_capacity = 0;  // frames
+  std::mutex mu;
+};
+
+namespace {
+
+void FreeHandle(kmc_b200_handle* h) {
+  if (!h) return;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  for (int s = 0; s < kmc_b200_handle::kSlots; ++s) {
+    if (h->d_in[s]) cudaFree(h->d_in[s]);
+    if (h->d_out[s]) cudaFree(h->d_out[s]);
+    if (h->h_in[s]) cudaFreeHost(h->h_in[s]);
+    if (h->h_out[s]) cudaFreeHost(h->h_out[s]);
+    if (h->done[s]) cudaEventDestroy(h->done[s]);
+    if (h->stream[s]) cudaStreamDestroy(h->stream[s]);
+  }
+  if (h->d_offsets) cudaFree(h->d_offsets);
+  if (h->d_params) cudaFree(h->d_params);
+  delete h;
+}
+
+int EnsureTables(kmc_b200_handle* h, int64_t n_frames) {
+  if (n_frames <= h->table_capacity) return KMC_B200_OK;
+  if (h->d_offsets) cudaFree(h->d_offsets);
+  if (h->d_params) cudaFree(h->d_params);
+  h->d_offsets = nullptr;
+  h->d_params = nullptr;
+  h->table_capacity = 0;
+  int64_t const cap = std::max<int64_t>(n_frames, 1024);
+  KMC_CUDA_TRY(cudaMalloc(&h->d_offsets, static_cast<size_t>(cap + 1) * sizeof(int64_t)));
+  KMC_CUDA_TRY(cudaMalloc(&h->d_params, static_cast<size_t>(cap) * sizeof(kmc_b200_frame_params)));
+  h->table_capacity = cap;
+  return KMC_B200_OK;
+}
+
+// Streams a host array through the device in capacity-sized chunks: stage (if pageable) -> H2D -> kernel -> D2H ->
+// unstage, three slots deep so the copy engines and the SMs overlap.  `launch(slot, chunk_first_point, chunk_points)`
+// enqueues the kernel for a chunk on h->stream[slot].
+template <class Launch>
+int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
+  constexpr int kSlots = kmc_b200_handle::kSlots;
+  bool const in_pinned = IsPinnedHost(in);
+  bool const out_pinned = IsPinnedHost(out);
+  struct Pending {
+    int64_t first = 0, count = 0;
+    bool active = false;
+  } pending[kSlots];
+
+  auto retire = [&](int slot) -> int {
+    if (!pending[slot].active) return KMC_B200_OK;
+    KMC_CUDA_TRY(cudaEventSynchronize(h->done[slot]));
+    if (!out_pinned)
+      std::memcpy(out + 4 * pending[slot].first, h->h_out[slot], static_cast<size_t>(pending[slot].count) * 16);
+    pending[slot].active = false;
+    return KMC_B200_OK;
+  };
+
+  int64_t chunk_index = 0;
+  for (int64_t first = 0; first < n; first += h->capacity, ++chunk_index) {
+    int const slot = static_cast<int>(chunk_index % kSlots);
+    int64_t const count = std::min(h->capacity, n - first);
+    size_t const bytes = static_cast<size_t>(count) * 16;
+    if (int rc = retire(slot)) return rc;
+    const float* src = in + 4 * first;
+    if (!in_pinned) {
+      std::memcpy(h->h_in[slot], src, bytes);
+      src = h->h_in[slot];
+    }
+    KMC_CUDA_TRY(cudaMemcpyAsync(h->d_in[slot], src, bytes, cudaMemcpyHostToDevice, h->stream[slot]));
+    if (int rc = launch(slot, first, count)) return rc;
+    float* dst = out_pinned ? out + 4 * first : h->h_out[slot];
+    KMC_CUDA_TRY(cudaMemcpyAsync(dst, h->d_out[slot], bytes, cudaMemcpyDeviceToHost, h->stream[slot]));
+    KMC_CUDA_TRY(cudaEventRecord(h->done[slot], h->stream[slot]));
+    pending[slot] = {first, count, true};
+  }
+  for (int k = 0; k < kSlots; ++k) {
+    int const slot = static_cast<int>((chunk_index + k) % kSlots);  // oldest first
+    if (int rc = retire(slot)) return rc;
+  }
+  return KMC_B200_OK;
+}
+
+int CheckOffsets(const int64_t* offsets, int32_t n_frames) {
+  if (offsets[0] != 0) return Fail(KMC_B200_ERR_BAD_SIZE, "frame_offsets[0] must be 0");
+  for (int32_t f = 0; f < n_frames; ++f)
+    if (offsets[f + 1] < offsets[f]) return Fail(KMC_B200_ERR_BAD_SIZE, "frame_offsets must be non-decreasing");
+  return KMC_B200_OK;
+}
+
+}  // namespace
+
+// =============================================================================================================
+// C ABI
+// =============================================================================================================
+extern "C" {
+
+int kmc_b200_version(void) { return KMC_B200_VERSION; }
+
+const char* kmc_b200_status_string(int status) {
+  switch (status) {
+    case KMC_B200_OK: return "ok";
+    case KMC_B200_ERR_NULL_POINTER: return "null pointer";
+    case KMC_B200_ERR_BAD_SIZE: return "bad size, offsets or alignment";
+    case KMC_B200_ERR_TIME_OUT_OF_RANGE: return "time outside the interpolation interval";
+    case KMC_B200_ERR_EMPTY_INTERVAL: return "t_end <= t_start";
+    case KMC_B200_ERR_NOT_RIGID: return "pose is not a finite rigid transform";
+    case KMC_B200_ERR_CUDA: return "CUDA error";
+    case KMC_B200_ERR_NO_DEVICE: return "no usable CUDA device";
+    case KMC_B200_ERR_BAD_MODE: return "unknown time mode";
+    case KMC_B200_ERR_CAPACITY: return "handle capacity exceeded";
+    case KMC_B200_ERR_IO: return "file I/O error";
+    default: return "unknown status";
+  }
+}
+
+const char* kmc_b200_last_error(void) { return t_last_error.c_str(); }
+
+int kmc_b200_device_count(void) {
+  int n = 0;
+  cudaError_t const e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return FailCuda(e, "cudaGetDeviceCount");
+  return n;
+}
+
+uint64_t kmc_b200_launch_count(void) { return kmc_b200::dev::LaunchCount(); }
+
+// ---- host prep ------------------------------------------------------------------------------------------------
+int kmc_b200_frame_params_from_twist(const double xi[6], double x_req, kmc_b200_frame_params* out) {
+  if (!xi || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "frame_params_from_twist: null argument");
+  for (int i = 0; i < 6; ++i)
+    if (!std::isfinite(xi[i])) return Fail(KMC_B200_ERR_NOT_RIGID, "frame_params_from_twist: non-finite twist");
+  if (!(x_req >= 0.0 && x_req <= 1.0))
+    return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "requested fraction outside [0, 1] (reference asserts, trajectory_interpolation.cpp:32)");
+  kmc_b200::host::FrameParamsFromTwist(xi, x_req, out);
+  return KMC_B200_OK;
+}
+
+int kmc_b200_frame_params_from_poses(const double T_start[16], const double T_end[16], double t_start, double t_end,
+                                     double t_req, kmc_b200_frame_params* out) {
+  if (!T_start || !T_end || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "frame_params_from_poses: null argument");
+  if (!(t_end > t_start)) return Fail(KMC_B200_ERR_EMPTY_INTERVAL, "t_end <= t_start (or NaN)");
+  if (!(t_req >= t_start && t_req <= t_end))
+    return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "requested time outside [t_start, t_end] (reference asserts, trajectory_interpolation.cpp:32)");
+  double xi[6];
+  if (!kmc_b200::host::RelativeTwist(T_start, T_end, xi))
+    return Fail(KMC_B200_ERR_NOT_RIGID, "T_start^-1 T_end has no proper-rotation polar factor");
+  kmc_b200::host::FrameParamsFromTwist(xi, (t_req - t_start) / (t_end - t_start), out);
+  return KMC_B200_OK;
+}
+
+#define KMC_NULLCHECK2(a, b) \
+  if (!(a) || !(b)) return Fail(KMC_B200_ERR_NULL_POINTER, std::string(__func__) + ": null argument")
+
+int kmc_b200_so3_hat(const double phi[3], double out[9]) { KMC_NULLCHECK2(phi, out); kmc_b200::host::So3Hat(phi, out); return KMC_B200_OK; }
+int kmc_b200_so3_vee(const double m[9], double out[3]) { KMC_NULLCHECK2(m, out); kmc_b200::host::So3Vee(m, out); return KMC_B200_OK; }
+int kmc_b200_so3_exp(const double phi[3], double out[9]) { KMC_NULLCHECK2(phi, out); kmc_b200::host::So3Exp(phi, out); return KMC_B200_OK; }
+int kmc_b200_so3_log(const double R[9], double out[3]) { KMC_NULLCHECK2(R, out); kmc_b200::host::So3Log(R, out); return KMC_B200_OK; }
+int kmc_b200_so3_left_jacobian(const double phi[3], double out[9]) { KMC_NULLCHECK2(phi, out); kmc_b200::host::So3LeftJacobian(phi, out); return KMC_B200_OK; }
+int kmc_b200_so3_inverse_left_jacobian(const double phi[3], double out[9]) { KMC_NULLCHECK2(phi, out); kmc_b200::host::So3InverseLeftJacobian(phi, out); return KMC_B200_OK; }
+int kmc_b200_se3_exp(const double xi[6], double T[16]) { KMC_NULLCHECK2(xi, T); kmc_b200::host::Se3Exp(xi, T); return KMC_B200_OK; }
+int kmc_b200_se3_log(const double T[16], double xi[6]) {
+  KMC_NULLCHECK2(T, xi);
+  if (!kmc_b200::host::Se3Log(T, xi)) return Fail(KMC_B200_ERR_NOT_RIGID, "se3_log: linear block has no proper-rotation polar factor");
+  return KMC_B200_OK;
+}
+
+int kmc_b200_pose_at_time(double t1, const double P1[16], double t2, const double P2[16], double t, double out[16]) {
+  if (!P1 || !P2 || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "pose_at_time: null argument");
+  int const rc = kmc_b200::host::PoseAtTime(t1, P1, t2, P2, t, out);
+  if (rc != KMC_B200_OK) return Fail(rc, std::string("pose_at_time: ") + kmc_b200_status_string(rc));
+  return rc;
+}
+
+int kmc_b200_relative_pose_between_times(double t1, const double P1[16], double t2, const double P2[16], double anchor,
+                                         double query, double out[16]) {
+  if (!P1 || !P2 || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "relative_pose_between_times: null argument");
+  double a[16], q[16], ainv[16];
+  int rc = kmc_b200::host::PoseAtTime(t1, P1, t2, P2, anchor, a);
+  if (rc == KMC_B200_OK) rc = kmc_b200::host::PoseAtTime(t1, P1, t2, P2, query, q);
+  if (rc != KMC_B200_OK) return Fail(rc, std::string("relative_pose_between_times: ") + kmc_b200_status_string(rc));
+  if (!kmc_b200::host::AffineInverse(a, ainv)) return Fail(KMC_B200_ERR_NOT_RIGID, "anchor pose is singular");
+  kmc_b200::host::AffineMul(ainv, q, out);
+  return KMC_B200_OK;
+}
+
+double kmc_b200_fraction_of_scan_completed(double x, double y) { return kmc_b200::host::FractionOfScanCompleted(x, y); }
+double kmc_b200_pseudo_time_stamp(double x, double y, double scan_start, double scan_end) {
+  return scan_start + kmc_b200::host::FractionOfScanCompleted(x, y) * (scan_end - scan_start);
+}
+
+int kmc_b200_shard_range(int64_t n_items, int32_t n_parts, int32_t index, int64_t* begin, int64_t* end) {
+  if (!begin || !end) return Fail(KMC_B200_ERR_NULL_POINTER, "shard_range: null argument");
+  if (n_items < 0 || n_parts <= 0 || index < 0 || index >= n_parts) return Fail(KMC_B200_ERR_BAD_SIZE, "shard_range: bad arguments");
+  // the first (n_items % n_parts) parts get one extra item
+  int64_t const base = n_items / n_parts, extra = n_items % n_parts;
+  *begin = index * base + std::min<int64_t>(index, extra);
+  *end = *begin + base + (index < extra ? 1 : 0);
+  return KMC_B200_OK;
+}
+
+// ---- device entry points ------------------------------------------------------------------------------------------
+int kmc_b200_deskew_frame_device(const float* in, float* out, int64_t n, const kmc_b200_frame_params* params, int mode,
+                                 void* stream) {
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_frame_device: negative n_points");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_frame_device: unknown time mode");
+  if (!params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_device: null params");
+  if (n == 0) return KMC_B200_OK;
+  if (!in || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_device: null point buffer");
+  if (!Aligned(in, 16) || !Aligned(out, 16)) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_frame_device: buffers must be 16-byte aligned");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  auto const cfg = kmc_b200::dev::PickConfig(n, Aligned(in, 32) && Aligned(out, 32), in == out, sm);
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(in, out, n, *params, mode, cfg, sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
+int kmc_b200_deskew_batch_device(const float* in, float* out, const int64_t* offsets_dev, const kmc_b200_frame_params* params_dev,
+                                 int32_t n_frames, int64_t n_total, int mode, void* stream) {
+  if (n_frames < 0 || n_total < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_device: negative size");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_batch_device: unknown time mode");
+  if (n_frames == 0 || n_total == 0) return KMC_B200_OK;
+  if (!in || !out || !offsets_dev || !params_dev) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_device: null argument");
+  if (!Aligned(in, 16) || !Aligned(out, 16) || !Aligned(params_dev, 16) || !Aligned(offsets_dev, 8))
+    return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_device: misaligned buffer");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  auto const cfg = kmc_b200::dev::PickConfig(n_total, Aligned(in, 32) && Aligned(out, 32), in == out, sm);
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(in, out, offsets_dev, params_dev, n_frames, n_total, 0, n_total, mode, cfg, sm,
+                                                static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
+int kmc_b200_pseudo_time_stamps_device(const float* in, double* stamps, int64_t n, double start, double end, void* stream) {
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_device: negative n_points");
+  if (n == 0) return KMC_B200_OK;
+  if (!in || !stamps) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_device: null argument");
+  if (!Aligned(in, 16) || !Aligned(stamps, 8)) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_device: misaligned buffer");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchPseudoTimeStamps(in, stamps, n, start, end, sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
+int kmc_b200_synth_scans_device(float* out, int64_t points_per_scan, int32_t n_scans, int32_t n_rings, uint64_t seed,
+                                int64_t first_scan_index, void* stream) {
+  if (points_per_scan < 0 || n_scans < 0 || n_rings < 2) return Fail(KMC_B200_ERR_BAD_SIZE, "synth_scans_device: bad size");
+  if (points_per_scan == 0 || n_scans == 0) return KMC_B200_OK;
+  if (!out) return Fail(KMC_B200_ERR_NULL_POINTER, "synth_scans_device: null output");
+  if (!Aligned(out, 16)) return Fail(KMC_B200_ERR_BAD_SIZE, "synth_scans_device: misaligned buffer");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchSynthScans(out, points_per_scan, n_scans, n_rings, seed, first_scan_index, sm,
+                                               static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
+int kmc_b200_synth_frame_params(int32_t n_frames, uint64_t seed, int64_t first_scan_index, double x_req,
+                                kmc_b200_frame_params* params_out, double* xi_out) {
+  if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "synth_frame_params: negative n_frames");
+  if (!params_out && n_frames > 0) return Fail(KMC_B200_ERR_NULL_POINTER, "synth_frame_params: null output");
+  if (!(x_req >= 0.0 && x_req <= 1.0)) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "synth_frame_params: x_req outside [0,1]");
+  for (int32_t k = 0; k < n_frames; ++k) {
+    uint64_t state = Mix(seed + static_cast<uint64_t>(first_scan_index + k)) ^ 0x5DEECE66Dull;
+    double xi[6];
+    xi[0] = 3.0 * Uniform01(state);   // forward motion per scan, up to 30 m/s
+    xi[1] = 0.05 * Normal(state);
+    xi[2] = 0.02 * Normal(state);
+    xi[3] = 0.003 * Normal(state);    // roll
+    xi[4] = 0.004 * Normal(state);    // pitch
+    xi[5] = 0.05 * Normal(state);     // yaw per scan (0.5 rad/s sigma)
+    kmc_b200::host::FrameParamsFromTwist(xi, x_req, params_out + k);
+    if (xi_out) std::memcpy(xi_out + 6 * k, xi, sizeof(xi));
+  }
+  return KMC_B200_OK;
+}
+
+// ---- handle ---------------------------------------------------------------------------------------------------------
+int kmc_b200_handle_create(int device, int64_t capacity_points, kmc_b200_handle** out) {
+  if (!out) return Fail(KMC_B200_ERR_NULL_POINTER, "handle_create: null output");
+  *out = nullptr;
+  if (capacity_points <= 0) return Fail(KMC_B200_ERR_BAD_SIZE, "handle_create: capacity must be positive");
+  int n_dev = kmc_b200_device_count();
+  if (n_dev < 0) return n_dev;
+  if (device < 0 || device >= n_dev) return Fail(KMC_B200_ERR_NO_DEVICE, "handle_create: no such device");
+  auto* h = new kmc_b200_handle;
+  h->device = device;
+  h->capacity = (capacity_points + 7) & ~int64_t{7};  // even point count per chunk keeps 256-bit accesses aligned
+  cudaError_t e = cudaSetDevice(device);
+  int rc = (e == cudaSuccess) ? SmCount(device, &h->sm_count) : FailCuda(e, "cudaSetDevice");
+  size_t const bytes = static_cast<size_t>(h->capacity) * 16;
+  for (int s = 0; s < kmc_b200_handle::kSlots && rc == KMC_B200_OK; ++s) {
+    if ((e = cudaStreamCreateWithFlags(&h->stream[s], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->done[s], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_in[s], bytes)) != cudaSuccess || (e = cudaMalloc(&h->d_out[s], bytes)) != cudaSuccess ||
+        (e = cudaMallocHost(&h->h_in[s], bytes)) != cudaSuccess || (e = cudaMallocHost(&h->h_out[s], bytes)) != cudaSuccess)
+      rc = FailCuda(e, "handle_create: allocating streams/buffers");
+  }
+  if (rc != KMC_B200_OK) {
+    std::string const keep = t_last_error;
+    FreeHandle(h);
+    t_last_error = keep;
+    return rc;
+  }
+  *out = h;
+  return KMC_B200_OK;
+}
+
+int kmc_b200_handle_destroy(kmc_b200_handle* h) {
+  FreeHandle(h);
+  return KMC_B200_OK;
+}
+
+int kmc_b200_handle_device(const kmc_b200_handle* h) { return h ? h->device : KMC_B200_ERR_NULL_POINTER; }
+int64_t kmc_b200_handle_capacity(const kmc_b200_handle* h) { return h ? h->capacity : KMC_B200_ERR_NULL_POINTER; }
+
+// ---- host entry points -------------------------------------------------------------------------------------------------
+int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, int64_t n, const kmc_b200_frame_params* params,
+                               int mode) {
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_host: null handle");
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_frame_host: negative n_points");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_frame_host: unknown time mode");
+  if (!params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_host: null params");
+  if (n == 0) return KMC_B200_OK;
+  if (!in || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_host: null point buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  KMC_CUDA_TRY(cudaSetDevice(h->device));
+  kmc_b200_frame_params const P = *params;
+  return StreamThroughDevice(h, in, out, n, [&](int slot, int64_t, int64_t count) -> int {
+    auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(h->d_in[slot], h->d_out[slot], count, P, mode, cfg, h->sm_count, h->stream[slot]));
+    return KMC_B200_OK;
+  });
+}
+
+int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* in, float* out, const int64_t* offsets,
+                               const kmc_b200_frame_params* params, int32_t n_frames, int mode) {
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_host: null handle");
+  if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_host: negative n_frames");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_batch_host: unknown time mode");
+  if (n_frames == 0) return KMC_B200_OK;
+  if (!offsets || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_host: null table");
+  if (int rc = CheckOffsets(offsets, n_frames)) return rc;
+  int64_t const n_total = offsets[n_frames];
+  if (n_total == 0) return KMC_B200_OK;
+  if (!in || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_host: null point buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  KMC_CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = EnsureTables(h, n_frames)) return rc;
+  // tables go up once, on slot 0's stream; the other slots wait for them through an event
+  KMC_CUDA_TRY(cudaMemcpyAsync(h->d_offsets, offsets, static_cast<size_t>(n_frames + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream[0]));
+  KMC_CUDA_TRY(cudaMemcpyAsync(h->d_params, params, static_cast<size_t>(n_frames) * sizeof(kmc_b200_frame_params), cudaMemcpyHostToDevice, h->stream[0]));
+  KMC_CUDA_TRY(cudaStreamSynchronize(h->stream[0]));
+  return StreamThroughDevice(h, in, out, n_total, [&](int slot, int64_t first, int64_t count) -> int {
+    auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[slot], h->d_out[slot], h->d_offsets, h->d_params, n_frames, count, first,
+                                                  n_total, mode, cfg, h->sm_count, h->stream[slot]));
+    return KMC_B200_OK;
+  });
+}
+
+int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_handles, const float* in, float* out,
+                                    const int64_t* offsets, const kmc_b200_frame_params* params, int32_t n_frames, int mode) {
+  if (!handles || n_handles <= 0) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_multi_gpu: no handles");
+  if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_multi_gpu: negative n_frames");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_batch_multi_gpu: unknown time mode");
+  if (n_frames == 0) return KMC_B200_OK;
+  if (!offsets || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_multi_gpu: null table");
+  for (int32_t i = 0; i < n_handles; ++i) {
+    if (!handles[i]) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_multi_gpu: null handle");
+    for (int32_t j = 0; j < i; ++j)
+      if (handles[j]->device == handles[i]->device)
+        return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_multi_gpu: handles must live on distinct devices");
+  }
+  if (int rc = CheckOffsets(offsets, n_frames)) return rc;
+  std::vector<int> status(static_cast<size_t>(n_handles), KMC_B200_OK);
+  std::vector<std::string> message(static_cast<size_t>(n_handles));
+  std::vector<std::thread> workers;
+  for (int32_t i = 0; i < n_handles; ++i) {
+    workers.emplace_back([&, i] {
+      int64_t fb = 0, fe = 0;
+      kmc_b200_shard_range(n_frames, n_handles, i, &fb, &fe);
+      if (fe <= fb) return;
+      std::vector<int64_t> local(static_cast<size_t>(fe - fb + 1));
+      for (int64_t f = fb; f <= fe; ++f) local[static_cast<size_t>(f - fb)] = offsets[f] - offsets[fb];
+      status[i] = kmc_b200_deskew_batch_host(handles[i], in ? in + 4 * offsets[fb] : nullptr, out ? out + 4 * offsets[fb] : nullptr,
+                                             local.data(), params + fb, static_cast<int32_t>(fe - fb), mode);
+      if (status[i] != KMC_B200_OK) message[i] = t_last_error;
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (int32_t i = 0; i < n_handles; ++i)
+    if (status[i] != KMC_B200_OK) return Fail(status[i], "device " + std::to_string(handles[i]->device) + ": " + message[i]);
+  return KMC_B200_OK;
+}
+
+int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out, const kmc_b200_frame_params* params,
+                             int64_t* n_points_out) {
+  if (!h || !path_in || !path_out || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_file: null argument");
+  FILE* f = std::fopen(path_in, "rb");
+  if (!f) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path_in);
+  std::fseek(f, 0, SEEK_END);
+  long const size = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  if (size < 0 || size % 16 != 0) {
+    std::fclose(f);
+    return Fail(KMC_B200_ERR_IO, std::string("KITTI pointcloud binary file is not a whole number of xyzi points: ") + path_in);
+  }
+  int64_t const n = size / 16;
+  std::vector<float> buf(static_cast<size_t>(4 * n)), res(static_cast<size_t>(4 * n));
+  size_t const got = n ? std::fread(buf.data(), 16, static_cast<size_t>(n), f) : 0;
+  std::fclose(f);
+  if (static_cast<int64_t>(got) != n) return Fail(KMC_B200_ERR_IO, std::string("short read: ") + path_in);
+  if (int rc = kmc_b200_deskew_frame_host(h, buf.data(), res.data(), n, params, KMC_B200_TIME_FROM_AZIMUTH)) return rc;
+  FILE* g = std::fopen(path_out, "wb");
+  if (!g) return Fail(KMC_B200_ERR_IO, std::string("unable to create output file: ") + path_out);
+  size_t const put = n ? std::fwrite(res.data(), 16, static_cast<size_t>(n), g) : 0;
+  bool const closed = (std::fclose(g) == 0);
+  if (static_cast<int64_t>(put) != n || !closed) return Fail(KMC_B200_ERR_IO, std::string("short write: ") + path_out);
+  if (n_points_out) *n_points_out = n;
+  return KMC_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,541 @@
+// kmc_kernels.cu — hand-written sm_100a kernels of the LiDAR deskew path.
+//
+// One fused streaming kernel replaces, per point, the reference's
+//   GetPseudoTimeStamps            timestamp_mocking.cpp:46-63   (azimuth -> fraction of scan)
+//   TrajectoryInterpolator         trajectory_interpolation.cpp:31-51 (fraction -> interpolated pose, relative pose)
+//   lie::Exp                       lie_algebra.cpp:22-35,51-65,83-92  (Rodrigues + left Jacobian)
+//   MotionCompensatePoint          motion_compensation.cpp:9-14  (rigid transform apply)
+// Everything that does not depend on the point (Log(T_start^-1 T_end) and the constants derived from it) is computed
+// once per frame on the host in double (kmc_host_math.cpp) and reaches the kernel as a 64-byte record.
+//
+// Math.  With xi = [rho; phi] the twist of the whole scan and s = x_i - x_req the signed fraction of
+// the scan between the requested time and the point's capture time, the reference's
+//   correction = GetPoseAtTime(t_req)^-1 GetPoseAtTime(t_i) = Exp(x_req xi)^-1 Exp(x_i xi) = Exp(s xi)
+// and  p' = R(s phi) p + J(s phi) s rho.  Written as a DISPLACEMENT so that fp32 keeps 1e-6 m at 120 m range:
+//   S = sin(s th)/th,  C = (1 - cos(s th))/th^2
+//   delta = C (phi (phi.p) - th^2 p + phi x rho) + S (phi x p + rho_perp) + s rho_par
+//   p'    = p + delta                                  (one rounding at the magnitude of p)
+// S and C come from a power series in (s th)^2 (no division, exact limit at th -> 0, which is the reference's own
+// golden test), or from half-angle polynomials valid to pi when a scan rotates by more than 1 rad.
+//
+// Memory: the N x 4 float32 "x y z i" array is read once and written once (32 B/point), 128-bit or 256-bit
+// (sm_100 LDG.256/STG.256) accesses, fully coalesced, several independent loads in flight per thread, persistent grid
+// sized in multiples of the SM count.  HBM-bandwidth bound; no shared memory, no tensor cores (nothing to contract).
+#include "kmc_kernels.cuh"
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+
+namespace kmc_b200::dev {
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+// ---------------------------------------------------------------------------------------------------------------
+// memory access helpers
+// ---------------------------------------------------------------------------------------------------------------
+struct alignas(32) Point2 {
+  float4 a, b;
+};
+
+template <int HINT>
+__device__ __forceinline__ float4 LoadPoint(const float4* p) {
+  float4 v;
+  if constexpr (HINT == 1) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+  } else if constexpr (HINT == 2) {
+    asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  } else {
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  }
+  return v;
+}
+
+template <int HINT>
+__device__ __forceinline__ void StorePoint(float4* p, float4 v) {
+  if constexpr (HINT == 1) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  } else if constexpr (HINT == 2) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  } else {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+
+// 256-bit accesses: two consecutive points per instruction (PTX ISA 8.8, sm_100+: SASS LDG.E.256 / STG.E.256).
+template <int HINT>
+__device__ __forceinline__ Point2 LoadPoint2(const float4* p) {
+  Point2 v;
+  if constexpr (HINT == 1) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+                 : "l"(p));
+  } else if constexpr (HINT == 2) {
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+                 : "l"(p));
+  } else {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+                 : "l"(p));
+  }
+  return v;
+}
+
+template <int HINT>
+__device__ __forceinline__ void StorePoint2(float4* p, const Point2& v) {
+  if constexpr (HINT == 1) {
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.a.x), "f"(v.a.y),
+                 "f"(v.a.z), "f"(v.a.w), "f"(v.b.x), "f"(v.b.y), "f"(v.b.z), "f"(v.b.w)
+                 : "memory");
+  } else if constexpr (HINT == 2) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.a.x), "f"(v.a.y), "f"(v.a.z),
+                 "f"(v.a.w), "f"(v.b.x), "f"(v.b.y), "f"(v.b.z), "f"(v.b.w)
+                 : "memory");
+  } else {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.a.x), "f"(v.a.y), "f"(v.a.z),
+                 "f"(v.a.w), "f"(v.b.x), "f"(v.b.y), "f"(v.b.z), "f"(v.b.w)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-point math
+// ---------------------------------------------------------------------------------------------------------------
+
+// atan2(y, x) / (2 pi) in "turns", in (-0.5, 0.5], with atan2's signed-zero conventions (the real scan contains
+// y == -0.0f, x < 0, which the reference maps to fraction 1.0; SURVEY 8c edge case i).
+// atan(r)/(2 pi r) on [0,1] as a degree-7 minimax polynomial in r^2 (|err| < 6e-9 turns in exact arithmetic,
+// < 3e-8 turns = 1.7e-7 rad evaluated in fp32).
+__device__ __forceinline__ float Atan2Turns(float y, float x) {
+  float const ax = fabsf(x), ay = fabsf(y);
+  float const mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(mx));  // one MUFU.RCP, 1 ulp
+  // atan2(+-0, +-0) must not produce 0 * inf; points closer than 1e-30 m to the spin axis count as on an axis.
+  float const r = (mx > 1e-30f) ? mn * inv : 0.0f;
+  float const t = r * r;
+  float p = -6.453042151e-04f;
+  p = fmaf(p, t, 3.479597159e-03f);
+  p = fmaf(p, t, -8.898722008e-03f);
+  p = fmaf(p, t, 1.534603257e-02f);
+  p = fmaf(p, t, -2.213627100e-02f);
+  p = fmaf(p, t, 3.174594417e-02f);
+  p = fmaf(p, t, -5.304612219e-02f);
+  p = fmaf(p, t, 1.591548324e-01f);
+  float q = r * p;                                    // [0, 1/8]
+  q = (ay > ax) ? (0.25f - q) : q;                    // [0, 1/4]
+  q = (__float_as_uint(x) >> 31) ? (0.5f - q) : q;    // sign BIT of x: atan2(+-0, -0) = +-pi
+  return copysignf(q, y);
+}
+
+// S = sin(s th)/th and C = (1 - cos(s th))/th^2 for x2 = (s th)^2 <= 1, as s*P(x2) and s^2*Q(x2).
+__device__ __forceinline__ void SeriesSC(float s, float s2, float x2, float& S, float& C) {
+  float ps = 2.755731922e-06f;  // 1/9!
+  ps = fmaf(ps, x2, -1.984126984e-04f);
+  ps = fmaf(ps, x2, 8.333333333e-03f);
+  ps = fmaf(ps, x2, -1.666666667e-01f);
+  ps = fmaf(ps, x2, 1.0f);
+  float pc = 2.755731922e-07f;  // 1/10!
+  pc = fmaf(pc, x2, -2.480158730e-05f);
+  pc = fmaf(pc, x2, 1.388888889e-03f);
+  pc = fmaf(pc, x2, -4.166666667e-02f);
+  pc = fmaf(pc, x2, 0.5f);
+  S = s * ps;
+  C = s2 * pc;
+}
+
+// The same S and C for any scan rotation up to pi: with y = s th / 2 (|y| <= pi/2),
+//   hs = sin(y)/th = (s/2) Ps(y^2),  ch = cos(y) = Pc(y^2),  S = 2 hs ch,  C = 2 hs^2      (no division by th either)
+// Taylor to y^13 / y^14: truncation < 7e-10 at |y| = pi/2.  Taken only when a scan rotates by more than 1 rad.
+__device__ __forceinline__ void HalfAngleSC(float s, float x2, float& S, float& C) {
+  float const y2 = 0.25f * x2;
+  float ps = 1.605904384e-10f;  // 1/13!
+  ps = fmaf(ps, y2, -2.505210839e-08f);
+  ps = fmaf(ps, y2, 2.755731922e-06f);
+  ps = fmaf(ps, y2, -1.984126984e-04f);
+  ps = fmaf(ps, y2, 8.333333333e-03f);
+  ps = fmaf(ps, y2, -1.666666667e-01f);
+  ps = fmaf(ps, y2, 1.0f);
+  float pc = -1.147074560e-11f;  // -1/14!
+  pc = fmaf(pc, y2, 2.087675699e-09f);
+  pc = fmaf(pc, y2, -2.755731922e-07f);
+  pc = fmaf(pc, y2, 2.480158730e-05f);
+  pc = fmaf(pc, y2, -1.388888889e-03f);
+  pc = fmaf(pc, y2, 4.166666667e-02f);
+  pc = fmaf(pc, y2, -0.5f);
+  pc = fmaf(pc, y2, 1.0f);
+  float const hs = (0.5f * s) * ps;
+  S = 2.0f * hs * pc;
+  C = 2.0f * hs * hs;
+}
+
+template <int MODE>
+__device__ __forceinline__ float4 DeskewPoint(float4 p, const kmc_b200_frame_params& P) {
+  float s;
+  if constexpr (MODE == KMC_B200_TIME_FROM_AZIMUTH) {
+    // frac = (pi - atan2(y,x)) / 2pi = 0.5 - turns ;  s = frac - x_req = c0 - turns
+    s = P.c0 - Atan2Turns(p.y, p.x);
+  } else {
+    s = p.w - P.x_req;
+  }
+  float const s2 = s * s;
+  float S, C;
+  if (P.wide == 0.0f) {  // frame-uniform branch
+    SeriesSC(s, s2, s2 * P.theta2, S, C);
+  } else {
+    HalfAngleSC(s, s2 * P.theta2, S, C);
+  }
+  float const d = fmaf(P.phi[2], p.z, fmaf(P.phi[1], p.y, P.phi[0] * p.x));
+  // u = phi (phi.p) - th^2 p + phi x rho
+  float const ux = fmaf(P.phi[0], d, fmaf(-P.theta2, p.x, P.phi_x_rho[0]));
+  float const uy = fmaf(P.phi[1], d, fmaf(-P.theta2, p.y, P.phi_x_rho[1]));
+  float const uz = fmaf(P.phi[2], d, fmaf(-P.theta2, p.z, P.phi_x_rho[2]));
+  // v = phi x p + rho_perp
+  float const vx = fmaf(P.phi[1], p.z, fmaf(-P.phi[2], p.y, P.rho_perp[0]));
+  float const vy = fmaf(P.phi[2], p.x, fmaf(-P.phi[0], p.z, P.rho_perp[1]));
+  float const vz = fmaf(P.phi[0], p.y, fmaf(-P.phi[1], p.x, P.rho_perp[2]));
+  float const dx = fmaf(C, ux, fmaf(S, vx, s * P.rho_par[0]));
+  float const dy = fmaf(C, uy, fmaf(S, vy, s * P.rho_par[1]));
+  float const dz = fmaf(C, uz, fmaf(S, vz, s * P.rho_par[2]));
+  return make_float4(p.x + dx, p.y + dy, p.z + dz, p.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// A contiguous range [a, b) of points that all belong to one frame, processed by the whole CTA.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE, int VEC, int UNROLL, int HINT>
+__device__ __forceinline__ void ProcessRange(const float4* __restrict__ in, float4* __restrict__ out, int64_t a, int64_t b,
+                                             const kmc_b200_frame_params& P) {
+  int const tid = threadIdx.x;
+  if constexpr (VEC == 2) {
+    if (a & 1) {  // 256-bit accesses need an even point index (the base pointer is 32-byte aligned)
+      if (tid == 0 && a < b) StorePoint<HINT>(out + a, DeskewPoint<MODE>(LoadPoint<HINT>(in + a), P));
+      a += 1;
+    }
+  }
+  constexpr int64_t kTile = static_cast<int64_t>(kBlockThreads) * UNROLL * VEC;
+  int64_t base = a;
+  for (; base + kTile <= b; base += kTile) {
+    if constexpr (VEC == 2) {
+      Point2 v[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) v[j] = LoadPoint2<HINT>(in + base + 2 * (j * kBlockThreads + tid));
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        Point2 r;
+        r.a = DeskewPoint<MODE>(v[j].a, P);
+        r.b = DeskewPoint<MODE>(v[j].b, P);
+        StorePoint2<HINT>(out + base + 2 * (j * kBlockThreads + tid), r);
+      }
+    } else {
+      float4 v[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) v[j] = LoadPoint<HINT>(in + base + j * kBlockThreads + tid);
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) StorePoint<HINT>(out + base + j * kBlockThreads + tid, DeskewPoint<MODE>(v[j], P));
+    }
+  }
+  for (int64_t i = base + tid; i < b; i += kBlockThreads) StorePoint<HINT>(out + i, DeskewPoint<MODE>(LoadPoint<HINT>(in + i), P));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// single frame: per-frame constants as a __grid_constant__ parameter (constant bank, broadcast to every lane for free)
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE, int VEC, int UNROLL, int HINT>
+__global__ void __launch_bounds__(kBlockThreads)
+    DeskewFrameKernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t n, int64_t item_points,
+                      const __grid_constant__ kmc_b200_frame_params P) {
+  int64_t const n_items = (n + item_points - 1) / item_points;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int64_t const p0 = item * item_points;
+    int64_t const p1 = (p0 + item_points < n) ? (p0 + item_points) : n;
+    ProcessRange<MODE, VEC, UNROLL, HINT>(in, out, p0, p1, P);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// batch of frames stored back to back: per-frame records in a global table (10 000 frames x 64 B do not fit the 64 KB
+// constant bank).  A work item is cut at frame boundaries; each piece is processed with its frame's record, which one
+// coalesced 64-byte load per warp fetches (lanes 0-15, one float each) and __shfl_sync broadcasts to the warp.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ kmc_b200_frame_params LoadParamsWarpBroadcast(const kmc_b200_frame_params* __restrict__ table,
+                                                                        int frame) {
+  int const lane = threadIdx.x & 31;
+  const float* rec = reinterpret_cast<const float*>(table + frame);
+  float const mine = __ldg(rec + (lane & 15));
+  kmc_b200_frame_params P;
+  float* dst = reinterpret_cast<float*>(&P);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) dst[k] = __shfl_sync(0xffffffffu, mine, k);
+  return P;
+}
+
+// largest f with offsets[f] <= p (offsets[n_frames] > p is guaranteed by the caller)
+__device__ __forceinline__ int LocateFrame(const int64_t* __restrict__ offsets, int n_frames, int64_t p, double frames_per_point) {
+  int guess = static_cast<int>(static_cast<double>(p) * frames_per_point);
+  guess = guess < 0 ? 0 : (guess > n_frames - 1 ? n_frames - 1 : guess);
+  if (__ldg(offsets + guess) <= p && p < __ldg(offsets + guess + 1)) return guess;
+  int lo = 0, hi = n_frames;
+  while (lo < hi) {
+    int const mid = (lo + hi + 1) >> 1;
+    if (__ldg(offsets + mid) <= p) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+template <int MODE, int VEC, int UNROLL, int HINT>
+__global__ void __launch_bounds__(kBlockThreads)
+    DeskewBatchKernel(const float4* __restrict__ in, float4* __restrict__ out, const int64_t* __restrict__ offsets,
+                      const kmc_b200_frame_params* __restrict__ table, int n_frames, int64_t n, int64_t item_points,
+                      int64_t point_base, double frames_per_point) {
+  int64_t const n_items = (n + item_points - 1) / item_points;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int64_t p0 = item * item_points;
+    int64_t const p1 = (p0 + item_points < n) ? (p0 + item_points) : n;
+    // in/out address the chunk [point_base, point_base + n) of the batch; offsets count from the start of the batch
+    int f = LocateFrame(offsets, n_frames, p0 + point_base, frames_per_point);
+    while (p0 < p1) {
+      int64_t const frame_end = __ldg(offsets + f + 1) - point_base;
+      if (frame_end <= p0) {  // empty frame
+        ++f;
+        continue;
+      }
+      int64_t const seg_end = frame_end < p1 ? frame_end : p1;
+      kmc_b200_frame_params const P = LoadParamsWarpBroadcast(table, f);
+      ProcessRange<MODE, VEC, UNROLL, HINT>(in, out, p0, seg_end, P);
+      p0 = seg_end;
+      ++f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GetPseudoTimeStamps (timestamp_mocking.cpp:56-63) in double, for callers that want the stamps themselves.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlockThreads)
+    PseudoTimeStampsKernel(const float4* __restrict__ in, double* __restrict__ stamps, int64_t n, double start, double duration) {
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; i < n; i += stride) {
+    float4 const p = LoadPoint<1>(in + i);
+    double const frac = (3.14159265358979323846 - atan2(static_cast<double>(p.y), static_cast<double>(p.x))) /
+                        (2.0 * 3.14159265358979323846);
+    stamps[i] = start + frac * duration;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// seeded synthetic spinning-LiDAR scans, generated in HBM
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t SplitMix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+    SynthScansKernel(float4* __restrict__ out, int64_t points_per_scan, int64_t n_total, int n_rings, uint64_t seed,
+                     int64_t first_scan_index) {
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
+  int64_t const steps = (points_per_scan + n_rings - 1) / n_rings;  // azimuth steps per ring
+  float const el_top = (n_rings == 64) ? 2.0f : 15.0f;              // HDL-64E: +2.0 .. -24.8 deg; dense: +15 .. -25 deg
+  float const el_bot = (n_rings == 64) ? -24.8f : -25.0f;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; g < n_total; g += stride) {
+    int64_t const scan = g / points_per_scan;
+    int64_t const i = g - scan * points_per_scan;
+    int64_t const ring = i / steps;
+    int64_t const step = i - ring * steps;
+    uint64_t const h0 = SplitMix64(SplitMix64(seed + static_cast<uint64_t>(first_scan_index + scan)) ^ static_cast<uint64_t>(i));
+    uint64_t const h1 = SplitMix64(h0);
+    float const u_range = static_cast<float>(h0 >> 40) * (1.0f / 16777216.0f);            // [0,1)
+    float const u_jit = static_cast<float>((h0 >> 16) & 0xFFFFFF) * (1.0f / 16777216.0f);  // [0,1)
+    float const inten = static_cast<float>(h1 % 100u) * 0.01f;
+    float const range = 2.0f * expf(u_range * 4.0943445622f);  // log-uniform [2, 120)
+    float const el = (el_top + (el_bot - el_top) * (static_cast<float>(ring) / static_cast<float>(n_rings - 1))) * 0.01745329252f;
+    float const az = 6.283185307f * ((static_cast<float>(step) + u_jit) / static_cast<float>(steps));
+    float sa, ca, se, ce;
+    sincosf(az, &sa, &ca);
+    sincosf(el, &se, &ce);
+    out[g] = make_float4(range * ce * ca, range * ce * sa, range * se, inten);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE, int VEC, int UNROLL, int HINT>
+cudaError_t LaunchFrameT(const float* in, float* out, int64_t n, const kmc_b200_frame_params& P, const LaunchConfig& cfg,
+                         int sm_count, cudaStream_t stream) {
+  int64_t const tile = static_cast<int64_t>(kBlockThreads) * UNROLL * VEC;
+  int64_t const item_points = tile * cfg.item_tiles;
+  int64_t const n_items = (n + item_points - 1) / item_points;
+  int64_t grid = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm;
+  if (grid > n_items) grid = n_items;
+  if (grid < 1) grid = 1;
+  DeskewFrameKernel<MODE, VEC, UNROLL, HINT><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), n, item_points, P);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+template <int MODE, int VEC, int UNROLL, int HINT>
+cudaError_t LaunchBatchT(const float* in, float* out, const int64_t* offsets, const kmc_b200_frame_params* table,
+                         int32_t n_frames, int64_t n, int64_t point_base, int64_t n_batch_points, const LaunchConfig& cfg,
+                         int sm_count, cudaStream_t stream) {
+  int64_t const tile = static_cast<int64_t>(kBlockThreads) * UNROLL * VEC;
+  int64_t const item_points = tile * cfg.item_tiles;
+  int64_t const n_items = (n + item_points - 1) / item_points;
+  int64_t grid = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm;
+  if (grid > n_items) grid = n_items;
+  if (grid < 1) grid = 1;
+  double const frames_per_point = static_cast<double>(n_frames) / static_cast<double>(n_batch_points);
+  DeskewBatchKernel<MODE, VEC, UNROLL, HINT><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), offsets, table, n_frames, n, item_points,
+      point_base, frames_per_point);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t DispatchFrame(const float* in, float* out, int64_t n, const kmc_b200_frame_params& P, const LaunchConfig& cfg,
+                          int sm, cudaStream_t st) {
+#define KMC_FRAME_CALL(V, U)                                                        \
+  switch (cfg.hint) {                                                               \
+    case 0: return LaunchFrameT<MODE, V, U, 0>(in, out, n, P, cfg, sm, st);         \
+    case 1: return LaunchFrameT<MODE, V, U, 1>(in, out, n, P, cfg, sm, st);         \
+    default: return LaunchFrameT<MODE, V, U, 2>(in, out, n, P, cfg, sm, st);        \
+  }
+  if (cfg.vec == 2) {
+    if (cfg.unroll >= 4) { KMC_FRAME_CALL(2, 4) }
+    if (cfg.unroll >= 2) { KMC_FRAME_CALL(2, 2) }
+    KMC_FRAME_CALL(2, 1)
+  }
+  if (cfg.unroll >= 4) { KMC_FRAME_CALL(1, 4) }
+  if (cfg.unroll >= 2) { KMC_FRAME_CALL(1, 2) }
+  KMC_FRAME_CALL(1, 1)
+#undef KMC_FRAME_CALL
+}
+
+template <int MODE>
+cudaError_t DispatchBatch(const float* in, float* out, const int64_t* offsets, const kmc_b200_frame_params* table,
+                          int32_t n_frames, int64_t n, int64_t base, int64_t nb, const LaunchConfig& cfg, int sm,
+                          cudaStream_t st) {
+#define KMC_BATCH_CALL(V, U)                                                                          \
+  switch (cfg.hint) {                                                                                 \
+    case 0: return LaunchBatchT<MODE, V, U, 0>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);    \
+    case 1: return LaunchBatchT<MODE, V, U, 1>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);    \
+    default: return LaunchBatchT<MODE, V, U, 2>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);   \
+  }
+  if (cfg.vec == 2) {
+    if (cfg.unroll >= 4) { KMC_BATCH_CALL(2, 4) }
+    if (cfg.unroll >= 2) { KMC_BATCH_CALL(2, 2) }
+    KMC_BATCH_CALL(2, 1)
+  }
+  if (cfg.unroll >= 4) { KMC_BATCH_CALL(1, 4) }
+  if (cfg.unroll >= 2) { KMC_BATCH_CALL(1, 2) }
+  KMC_BATCH_CALL(1, 1)
+#undef KMC_BATCH_CALL
+}
+
+void ApplyTuneEnv(LaunchConfig& cfg) {
+  const char* env = std::getenv("KMC_B200_TUNE");
+  if (!env || !*env) return;
+  char buf[256];
+  std::strncpy(buf, env, sizeof(buf) - 1);
+  buf[sizeof(buf) - 1] = 0;
+  for (char* tok = std::strtok(buf, ","); tok; tok = std::strtok(nullptr, ",")) {
+    char* eq = std::strchr(tok, '=');
+    if (!eq) continue;
+    *eq = 0;
+    int const v = std::atoi(eq + 1);
+    if (!std::strcmp(tok, "vec")) cfg.vec = v;
+    else if (!std::strcmp(tok, "unroll")) cfg.unroll = v;
+    else if (!std::strcmp(tok, "hint")) cfg.hint = v;
+    else if (!std::strcmp(tok, "ctas")) cfg.ctas_per_sm = v;
+    else if (!std::strcmp(tok, "item_tiles")) cfg.item_tiles = v;
+  }
+}
+
+}  // namespace
+
+uint64_t LaunchCount() { return g_launches.load(std::memory_order_relaxed); }
+
+LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_count) {
+  LaunchConfig cfg;
+  cfg.vec = 2;
+  cfg.unroll = 2;
+  cfg.hint = 1;
+  cfg.ctas_per_sm = 4;
+  cfg.item_tiles = 8;
+  // Small inputs are latency bound: spread them over as many CTAs as possible instead of deep per-thread unrolling.
+  int64_t const big = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm * kBlockThreads * cfg.unroll * cfg.vec * cfg.item_tiles;
+  if (n_points < big) {
+    cfg.item_tiles = 1;
+    int64_t const mid = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm * kBlockThreads * cfg.unroll * cfg.vec;
+    if (n_points < mid) {
+      cfg.vec = 1;
+      cfg.unroll = 1;
+    }
+  }
+  ApplyTuneEnv(cfg);
+  if (!aligned32) cfg.vec = 1;
+  if (in_place) cfg.hint = 0;  // the .nc path assumes the input is read-only for the whole kernel
+  if (cfg.vec != 2) cfg.vec = 1;
+  if (cfg.unroll < 1) cfg.unroll = 1;
+  if (cfg.hint < 0 || cfg.hint > 2) cfg.hint = 1;
+  if (cfg.ctas_per_sm < 1) cfg.ctas_per_sm = 1;
+  if (cfg.ctas_per_sm > 8) cfg.ctas_per_sm = 8;
+  if (cfg.item_tiles < 1) cfg.item_tiles = 1;
+  return cfg;
+}
+
+cudaError_t LaunchDeskewFrame(const float* in, float* out, int64_t n, const kmc_b200_frame_params& params, int mode,
+                              const LaunchConfig& cfg, int sm_count, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (mode == KMC_B200_TIME_FROM_AZIMUTH) return DispatchFrame<KMC_B200_TIME_FROM_AZIMUTH>(in, out, n, params, cfg, sm_count, stream);
+  return DispatchFrame<KMC_B200_TIME_FROM_W>(in, out, n, params, cfg, sm_count, stream);
+}
+
+cudaError_t LaunchDeskewBatch(const float* in, float* out, const int64_t* offsets_dev,
+                              const kmc_b200_frame_params* params_dev, int32_t n_frames, int64_t n_points,
+                              int64_t point_base, int64_t n_batch_points, int mode, const LaunchConfig& cfg, int sm_count,
+                              cudaStream_t stream) {
+  if (n_points <= 0 || n_frames <= 0) return cudaSuccess;
+  if (mode == KMC_B200_TIME_FROM_AZIMUTH)
+    return DispatchBatch<KMC_B200_TIME_FROM_AZIMUTH>(in, out, offsets_dev, params_dev, n_frames, n_points, point_base,
+                                                     n_batch_points, cfg, sm_count, stream);
+  return DispatchBatch<KMC_B200_TIME_FROM_W>(in, out, offsets_dev, params_dev, n_frames, n_points, point_base,
+                                             n_batch_points, cfg, sm_count, stream);
+}
+
+cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,
+                                   cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
+  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  if (grid > cap) grid = cap;
+  PseudoTimeStampsKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(reinterpret_cast<const float4*>(in), stamps, n,
+                                                                                    start, end - start);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchSynthScans(float* out, int64_t points_per_scan, int32_t n_scans, int32_t n_rings, uint64_t seed,
+                             int64_t first_scan_index, int sm_count, cudaStream_t stream) {
+  int64_t const n_total = points_per_scan * n_scans;
+  if (n_total <= 0) return cudaSuccess;
+  int64_t grid = (n_total + kBlockThreads - 1) / kBlockThreads;
+  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  if (grid > cap) grid = cap;
+  SynthScansKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(reinterpret_cast<float4*>(out), points_per_scan,
+                                                                              n_total, n_rings, seed, first_scan_index);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+}  // namespace kmc_b200::dev

@@ -1,0 +1,44 @@
+// kmc_kernels.cuh — launch interface of the sm_100a kernels (internal; the public boundary is include/kmc_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kmc_b200.h"
+
+namespace kmc_b200::dev {
+
+// Kernel shape knobs.  Defaults are chosen by PickConfig(); a sweep (tools/sweep.py) can override them through the
+// KMC_B200_TUNE environment variable ("vec=2,unroll=4,hint=1,ctas=4,item_tiles=8") without recompiling.
+struct LaunchConfig {
+  int vec;         // points per memory instruction: 1 = 128-bit LDG/STG, 2 = 256-bit LDG/STG (sm_100 only)
+  int unroll;      // memory instructions in flight per thread per tile (1, 2, 4)
+  int hint;        // 0 = plain ld/st, 1 = L1::no_allocate (+ .nc load), 2 = .cs streaming (evict-first)
+  int ctas_per_sm; // persistent grid = SMs * ctas_per_sm (capped by the number of work items)
+  int item_tiles;  // tiles per work item (a work item is the unit a CTA takes per scheduling step)
+};
+
+constexpr int kBlockThreads = 256;
+
+LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_count);
+
+cudaError_t LaunchDeskewFrame(const float* in, float* out, int64_t n, const kmc_b200_frame_params& params, int mode,
+                              const LaunchConfig& cfg, int sm_count, cudaStream_t stream);
+
+// in/out address the points [point_base, point_base + n_points) of a batch of n_batch_points points whose frame table
+// (offsets_dev, n_frames + 1 entries counted from the start of the batch) and records live in device memory.
+cudaError_t LaunchDeskewBatch(const float* in, float* out, const int64_t* offsets_dev,
+                              const kmc_b200_frame_params* params_dev, int32_t n_frames, int64_t n_points,
+                              int64_t point_base, int64_t n_batch_points, int mode, const LaunchConfig& cfg, int sm_count,
+                              cudaStream_t stream);
+
+cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,
+                                   cudaStream_t stream);
+
+cudaError_t LaunchSynthScans(float* out, int64_t points_per_scan, int32_t n_scans, int32_t n_rings, uint64_t seed,
+                             int64_t first_scan_index, int sm_count, cudaStream_t stream);
+
+// Number of kernel launches issued through this translation unit since process start (bench.py reports it).
+uint64_t LaunchCount();
+
+}  // namespace kmc_b200::dev

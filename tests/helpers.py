@@ -1,0 +1,116 @@
+"""Shared builders for the tests and bench.py's parity spot-checks: real scan, synthetic scans, frames, closed form."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+TOL_M = 1e-5  # BASELINE.json north_star: max |dxyz| < 1e-5 m per coordinate vs the reference's double result
+
+# T_end = T_start * Exp(CONFIG1_TWIST) — 13 m/s, 0.5 rad/s, deliberately aggressive.
+CONFIG1_TWIST = [1.34, 0.03, -0.01, -0.003, 0.004, 0.05]
+
+
+def kats() -> dict:
+    with open(os.path.join(GOLDEN, "reference_kats.json")) as f:
+        return json.load(f)
+
+
+def real_scan() -> np.ndarray:
+    """The reference's shipped KITTI scan (drive_0005 frame 0): (123397, 4) float32 xyzi."""
+    k = kats()["real_scan_frame0"]
+    pts = np.fromfile(os.path.join(GOLDEN, k["file"]), dtype=np.float32).reshape(-1, 4)
+    assert pts.shape[0] == k["num_points"]
+    return pts
+
+
+def oxts7(d: dict, stamp: float | None = None):
+    return [d.get("stamp", 0.0) if stamp is None else stamp, d["lat"], d["lon"], d["alt"], d["roll"], d["pitch"], d["yaw"]]
+
+
+def config1_frame():
+    """(T_start, T_end, stamp_start, stamp_middle, stamp_end) for BASELINE config 1 (real scan, Mercator-magnitude pose)."""
+    from oracle import binding as ob
+    k = kats()
+    r = k["real_scan_frame0"]
+    T_start = ob.oxts_to_pose(oxts7(k["oxts_to_pose"]["oxts"], r["oxts_stamp"]))
+    T_end = T_start @ ob.se3_exp(CONFIG1_TWIST)
+    return T_start, T_end, r["stamp_start"], r["stamp_middle"], r["stamp_end"]
+
+
+def synthetic_scan(n_points: int = 130_000, n_rings: int = 64, seed: int = 20110926, max_range: float = 120.0) -> np.ndarray:
+    """HDL-64E style scan: ring-major, azimuth increasing within a ring, log-uniform range in
+    [2, max_range) m, coordinates rounded to float32.  numpy generator — independent of the CUDA generator."""
+    rng = np.random.default_rng(seed)
+    steps = -(-n_points // n_rings)
+    i = np.arange(n_points)
+    ring, step = i // steps, i % steps
+    el_top, el_bot = (2.0, -24.8) if n_rings == 64 else (15.0, -25.0)
+    el = np.deg2rad(el_top + (el_bot - el_top) * ring / (n_rings - 1))
+    az = 2 * np.pi * (step + rng.uniform(0, 1, n_points)) / steps
+    r = 2.0 * np.exp(rng.uniform(0, 1, n_points) * np.log(max_range / 2.0))
+    pts = np.empty((n_points, 4), dtype=np.float32)
+    pts[:, 0] = r * np.cos(el) * np.cos(az)
+    pts[:, 1] = r * np.cos(el) * np.sin(az)
+    pts[:, 2] = r * np.sin(el)
+    pts[:, 3] = rng.integers(0, 100, n_points) * 0.01
+    return pts
+
+
+def random_twist(rng) -> np.ndarray:
+    """SURVEY 8d config 2 twist distribution: rho = (U(0,3), N(0,.05), N(0,.02)) m, phi = (N(0,.003), N(0,.004), N(0,.05)) rad."""
+    return np.array([rng.uniform(0, 3), rng.normal(0, 0.05), rng.normal(0, 0.02),
+                     rng.normal(0, 0.003), rng.normal(0, 0.004), rng.normal(0, 0.05)])
+
+
+def random_pose(rng, mercator: bool = False) -> np.ndarray:
+    from oracle import binding as ob
+    T = ob.se3_exp(np.concatenate([rng.normal(0, 10, 3), rng.normal(0, 0.7, 3)]))
+    if mercator:
+        T[:3, 3] += np.array([937631.25, 6276764.0, 112.8])
+    return T
+
+
+def edge_points() -> np.ndarray:
+    """SURVEY 8c edge cases: y = -0 / +0 with x < 0 (frac 1 / 0), x = y = 0, axis points, far points."""
+    return np.array([
+        [-17.173, -0.0, -1.81, 0.11],   # the real scan's own y == -0.0 point: frac == 1.0 exactly
+        [-17.173, 0.0, -1.81, 0.12],    # frac == 0.0
+        [0.0, 0.0, 1.5, 0.13],          # atan2(0, 0) = 0 -> frac 0.5, no NaN
+        [-0.0, 0.0, 1.5, 0.14],         # atan2(+0, -0) = +pi -> frac 0
+        [-0.0, -0.0, 1.5, 0.15],        # atan2(-0, -0) = -pi -> frac 1
+        [0.0, -0.0, 1.5, 0.16],
+        [5.0, 0.0, 0.0, 0.17], [0.0, 5.0, 0.0, 0.18], [0.0, -5.0, 0.0, 0.19], [-5.0, 1e-6, 0.0, 0.2], [-5.0, -1e-6, 0.0, 0.21],
+        [3.0, 3.0, -1.0, 0.22], [-3.0, 3.0, -1.0, 0.23], [-3.0, -3.0, -1.0, 0.24], [3.0, -3.0, -1.0, 0.25],
+        [119.9, 0.5, -20.0, 0.26], [-80.0, -90.0, 2.0, 0.27], [1e-3, -2e-3, 0.0, 0.28],
+    ], dtype=np.float32)
+
+
+def closed_form_deskew(xyzi: np.ndarray, xi: np.ndarray, x_req: float, frac: np.ndarray | None = None) -> np.ndarray:
+    """Double-precision numpy evaluation of p' = Exp((frac - x_req) xi) p — an independent cross-check of the oracle
+    (which follows the reference's literal GetPoseAtTime(t_req)^-1 GetPoseAtTime(t_i) product)."""
+    p = xyzi[:, :3].astype(np.float64)
+    if frac is None:
+        frac = (np.pi - np.arctan2(xyzi[:, 1].astype(np.float64), xyzi[:, 0].astype(np.float64))) / (2 * np.pi)
+    s = (frac - x_req)[:, None]
+    rho, phi = np.asarray(xi[:3], float), np.asarray(xi[3:], float)
+    th = np.linalg.norm(phi)
+    if th < 1e-12:
+        return p + s * rho + np.cross(np.broadcast_to(s * phi, p.shape), p)
+    a = phi / th
+    ang = s * th
+    sn, cs = np.sin(ang), np.cos(ang)
+    rot = cs * p + (1 - cs) * a * (p @ a)[:, None] + sn * np.cross(np.broadcast_to(a, p.shape), p)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        k1 = np.where(np.abs(ang) > 1e-12, sn / ang, 1.0)
+        k2 = np.where(np.abs(ang) > 1e-12, (1 - cs) / ang, 0.5 * ang)
+    trans = s * (k1 * rho + (1 - k1) * a * (a @ rho) + k2 * np.cross(a, rho))
+    return rot + trans
+
+
+def max_abs_err(out_xyzi: np.ndarray, ref_xyz1: np.ndarray) -> float:
+    return float(np.max(np.abs(out_xyzi[:, :3].astype(np.float64) - ref_xyz1[:, :3])))

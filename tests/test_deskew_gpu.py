@@ -1,0 +1,479 @@
+"""Parity of the CUDA deskew path (through the C ABI) against the CPU oracle.  Needs a B200: `pytest -m gpu`.
+
+Bar (BASELINE.json north_star): max |dxyz| < 1e-5 m per coordinate vs the reference's double-precision result on the
+same float32 inputs; the w (intensity) lane is bit-exact.  There is no CPU fallback: the `cuda` fixture fails the test
+outright if no device is visible.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import TOL_M
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def dev(torch, a: np.ndarray):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def run_frame(torch, capi, xyzi: np.ndarray, params, mode=0, in_place=False) -> np.ndarray:
+    d_in = dev(torch, xyzi.astype(np.float32))
+    d_out = d_in if in_place else torch.empty_like(d_in)
+    capi.deskew_frame_device(d_in.data_ptr(), d_out.data_ptr(), xyzi.shape[0], params, mode,
+                             torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+def run_batch(torch, capi, xyzi: np.ndarray, offsets, params_arr, mode=0) -> np.ndarray:
+    d_in = dev(torch, xyzi.astype(np.float32))
+    d_out = torch.empty_like(d_in)
+    d_off = dev(torch, np.asarray(offsets, dtype=np.int64))
+    d_par = dev(torch, params_arr.view(np.uint8))
+    capi.deskew_batch_device(d_in.data_ptr(), d_out.data_ptr(), d_off.data_ptr(), d_par.data_ptr(), len(params_arr),
+                             xyzi.shape[0], mode, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+def oracle_frame(oracle, xyzi, T_start, T_end, t0, t2, t_req):
+    return oracle.deskew_xyzi_scan(xyzi, T_start, T_end, t0, t2, t_req)
+
+
+def assert_parity(out, ref, xyzi, tol=TOL_M):
+    err = helpers.max_abs_err(out, ref)
+    assert err < tol, f"max |dxyz| = {err:.3e} m"
+    assert out[:, 3].tobytes() == np.ascontiguousarray(xyzi[:, 3], dtype=np.float32).tobytes(), "w lane must pass through bit-exactly"
+    return err
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_extension_is_the_loaded_native_library(capi, cuda):
+    assert os.path.samefile(capi.LIB_PATH, os.path.join(os.path.dirname(capi.__file__), "lib", "libkmc_b200.so"))
+    assert capi.lib().kmc_b200_device_count() >= 1
+    before = capi.launch_count()
+    p = capi.frame_params_from_twist([1, 0, 0, 0, 0, 0], 0.5)
+    run_frame(cuda, capi, helpers.edge_points(), p)
+    assert capi.launch_count() == before + 1
+
+
+def test_reference_golden_frame(capi, oracle, kats, cuda):
+    """test/test_motion_compensation.cpp:54-76 through the CUDA path: (-0.27829874, 5, 0), (5, 0, 0), (0.27829874, -5, 0)."""
+    from test_oracle_golden import float_eq, golden_frame
+    g, cloud, T_start, T_end = golden_frame(oracle, kats)
+    xyzi = cloud.astype(np.float32)
+    xyzi[:, 3] = [0.25, 0.5, 0.75]
+    p = capi.frame_params_from_poses(T_start, T_end, g["stamp_start"], g["stamp_end"], g["requested_time"])
+    out = run_frame(cuda, capi, xyzi, p)
+    for got, want in zip(out[:, :3].reshape(-1), np.array(g["expected"])[:, :3].reshape(-1)):
+        assert float_eq(got, want), (got, want)
+    assert np.array_equal(out[:, 3], xyzi[:, 3])
+
+
+@pytest.mark.parametrize("which_req", ["middle", "start", "end"])
+def test_config1_real_kitti_scan(capi, oracle, cuda, which_req):
+    """BASELINE config 1: the shipped 123 397-point scan, Mercator-magnitude start pose, aggressive motion."""
+    pts = helpers.real_scan()
+    T_start, T_end, t0, t1, t2 = helpers.config1_frame()
+    t_req = {"middle": t1, "start": t0, "end": t2}[which_req]
+    p = capi.frame_params_from_poses(T_start, T_end, t0, t2, t_req)
+    out = run_frame(cuda, capi, pts, p)
+    ref = oracle_frame(oracle, pts, T_start, T_end, t0, t2, t_req)
+    err = assert_parity(out, ref, pts)
+    print(f"config1[{which_req}] max|dxyz| = {err:.3e} m over {len(pts)} points")
+
+
+@pytest.mark.parametrize("seed", [20110926, 20110927, 20110928])
+@pytest.mark.parametrize("x_req", [0.5, 0.0, 1.0, 0.3])
+def test_config2_synthetic_130k_scan(capi, oracle, cuda, seed, x_req):
+    """BASELINE config 2: one 130 000-point HDL-64E style scan, random twist from SURVEY 8d, identity and Mercator poses."""
+    rng = np.random.default_rng(seed)
+    pts = helpers.synthetic_scan(130_000, 64, seed)
+    T_start = helpers.random_pose(rng, mercator=bool(seed % 2))
+    xi = helpers.random_twist(rng)
+    T_end = T_start @ oracle.se3_exp(xi)
+    t0, t2 = 0.0, 0.1
+    t_req = t0 + x_req * (t2 - t0)
+    p = capi.frame_params_from_poses(T_start, T_end, t0, t2, t_req)
+    out = run_frame(cuda, capi, pts, p)
+    # the oracle runs the literal reference algorithm at ~0.4 Mpoint/s: check every 4th point
+    sub = slice(seed % 4, None, 4)
+    ref = oracle_frame(oracle, pts[sub], T_start, T_end, t0, t2, t_req)
+    assert_parity(out[sub], ref, pts[sub])
+    # and every point against the independent double closed form
+    cf = helpers.closed_form_deskew(pts, xi, x_req)
+    assert np.abs(out[:, :3].astype(np.float64) - cf).max() < TOL_M
+
+
+SPECIAL_TWISTS = {
+    "zero": [0, 0, 0, 0, 0, 0],
+    "pure_translation_golden_like": [1.11319, 0, 0, 0, 0, 0],
+    "pure_rotation": [0, 0, 0, 0.01, -0.02, 0.08],
+    "tiny_rotation_below_taylor_switch": [1.0, 0.1, 0.0, 2e-7, -3e-7, 5e-7],
+    "general": [2.5, -0.08, 0.03, 0.004, -0.006, -0.07],
+    "fast_yaw": [1.0, 0.0, 0.0, 0.0, 0.0, 0.6],
+    "wide_path_over_1_rad": [0.5, 0.1, 0.0, 0.1, -0.2, 1.4],
+    "wide_path_near_pi": [0.2, 0.0, 0.1, 0.3, 0.2, 2.9],
+}
+
+
+@pytest.mark.parametrize("name", list(SPECIAL_TWISTS))
+def test_special_frames_and_edge_points(capi, oracle, cuda, name):
+    """SURVEY 8c edge cases: xi = 0, phi = 0, rho = 0, theta below the reference's 1e-6 Taylor switch, y = +-0 with x < 0,
+    x = y = 0, and scan rotations beyond 1 rad (kernel's half-angle path)."""
+    xi = np.array(SPECIAL_TWISTS[name], dtype=np.float64)
+    rng = np.random.default_rng(1)
+    pts = np.concatenate([helpers.edge_points(), helpers.synthetic_scan(20_000, 64, 5, max_range=40.0 if "wide" in name else 120.0)])
+    T_start = helpers.random_pose(rng)
+    T_end = T_start @ oracle.se3_exp(xi)
+    for x_req in (0.5, 0.0, 1.0):
+        p = capi.frame_params_from_poses(T_start, T_end, 100.0, 100.1, 100.0 + 0.1 * x_req)
+        out = run_frame(cuda, capi, pts, p)
+        ref = oracle_frame(oracle, pts, T_start, T_end, 100.0, 100.1, 100.0 + 0.1 * x_req)
+        # fp32 carries ~1e-7 of the displacement; beyond ~1 rad per scan displacements reach tens of metres
+        tol = TOL_M if "wide" not in name else 4e-5
+        assert_parity(out, ref, pts, tol)
+        assert not np.isnan(out).any()
+    if name == "zero":
+        assert out.tobytes() == pts.tobytes(), "zero motion must be the identity, bit for bit"
+
+
+def test_edge_point_fractions_exact(capi, oracle, cuda):
+    """With a pure unit translation and x_req = 0 the x displacement IS the fraction of scan completed:
+    y = -0, x < 0 -> 1.0 ; y = +0, x < 0 -> 0.0 ; x = y = 0 -> 0.5 (timestamp_mocking.cpp:46; SURVEY 8c i-iii)."""
+    pts = helpers.edge_points()
+    p = capi.frame_params_from_twist([1.0, 0, 0, 0, 0, 0], 0.0)
+    out = run_frame(cuda, capi, pts, p)
+    frac = out[:, 0].astype(np.float64) - pts[:, 0]
+    want = np.array([oracle.fraction_of_scan_completed([x, y, 0, 1]) for x, y in pts[:, :2].astype(np.float64)])
+    assert frac[0] == 1.0 and frac[1] == 0.0 and frac[2] == 0.5 and frac[3] == 0.0 and frac[4] == 1.0 and frac[5] == 0.5
+    assert np.abs(frac - want).max() < 2e-5  # x + frac rounds at the magnitude of x (up to 120 m)
+
+
+def test_time_from_w_mode_matches_reference_frame_call(capi, oracle, cuda):
+    """KMC_B200_TIME_FROM_W: w carries (t_i - t_start)/(t_end - t_start) for arbitrary per-point stamps — the contract
+    of MotionCompensateFrame(frame, t) with frame.scan.timestamps (motion_compensation.cpp:22-25)."""
+    rng = np.random.default_rng(21)
+    n = 30_000
+    pts = helpers.synthetic_scan(n, 64, 77)
+    t0, t2, t_req = 47072.28, 47072.38, 47072.31
+    stamps = rng.uniform(t0, t2, n)
+    stamps[:3] = [t0, t2, t_req]
+    T_start = helpers.random_pose(rng, mercator=True)
+    xi = helpers.random_twist(rng)
+    T_end = T_start @ oracle.se3_exp(xi)
+    cloud = np.concatenate([pts[:, :3].astype(np.float64), np.ones((n, 1))], axis=1)
+    ref = oracle.motion_compensate_frame(cloud, stamps, T_start, T_end, t0, t2, t_req)
+    xyzw = pts.copy()
+    xyzw[:, 3] = ((stamps - t0) / (t2 - t0)).astype(np.float32)
+    p = capi.frame_params_from_poses(T_start, T_end, t0, t2, t_req)
+    out = run_frame(cuda, capi, xyzw, p, mode=capi.TIME_FROM_W)
+    assert_parity(out, ref, xyzw)
+
+
+def test_in_place_equals_out_of_place(capi, cuda):
+    pts = helpers.synthetic_scan(50_001, 64, 3)
+    p = capi.frame_params_from_twist(helpers.CONFIG1_TWIST, 0.5)
+    a = run_frame(cuda, capi, pts, p)
+    b = run_frame(cuda, capi, pts, p, in_place=True)
+    assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 255, 256, 257, 1023, 1025, 4097, 100_003])
+def test_ragged_sizes_single_frame(capi, cuda, n):
+    """Tile tails and odd starts: every size must agree with the closed form and leave the guard region untouched."""
+    torch = cuda
+    pts = helpers.synthetic_scan(n, 64, n)
+    xi = np.array(helpers.CONFIG1_TWIST)
+    p = capi.frame_params_from_twist(xi, 0.5)
+    guard = 64
+    d_in = dev(torch, pts)
+    d_out = torch.full((n + guard, 4), 123.0, dtype=torch.float32, device="cuda")
+    capi.deskew_frame_device(d_in.data_ptr(), d_out.data_ptr(), n, p, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    assert np.all(out[n:] == 123.0), "wrote past the end of the scan"
+    assert np.abs(out[:n, :3] - helpers.closed_form_deskew(pts, xi, 0.5)).max() < TOL_M
+
+
+def test_unaligned_to_32_bytes_falls_back_to_128bit_accesses(capi, cuda):
+    """Device pointers only need 16-byte alignment; a 16-byte-offset view disables the 256-bit path, results identical."""
+    torch = cuda
+    pts = helpers.synthetic_scan(70_000, 64, 9)
+    p = capi.frame_params_from_twist(helpers.CONFIG1_TWIST, 0.5)
+    want = run_frame(torch, capi, pts, p)
+    buf_in = torch.zeros((pts.shape[0] + 1, 4), dtype=torch.float32, device="cuda")
+    buf_out = torch.zeros_like(buf_in)
+    buf_in[1:] = torch.from_numpy(pts).cuda()
+    assert buf_in[1:].data_ptr() % 32 == 16
+    capi.deskew_frame_device(buf_in[1:].data_ptr(), buf_out[1:].data_ptr(), pts.shape[0], p, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert buf_out[1:].cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_empty_scan_and_empty_batch(capi, cuda):
+    p = capi.frame_params_from_twist(helpers.CONFIG1_TWIST, 0.5)
+    capi.deskew_frame_device(0, 0, 0, p)
+    capi.deskew_batch_device(0, 0, 0, 0, 0, 0)
+
+
+def test_nan_and_inf_points_propagate(capi, oracle, cuda):
+    """non-finite coordinates give non-finite outputs exactly where the reference's do."""
+    pts = helpers.synthetic_scan(64, 64, 2)
+    pts[3, 0] = np.nan
+    pts[7, 1] = np.inf
+    pts[11, 2] = -np.inf
+    rng = np.random.default_rng(4)
+    T_start = helpers.random_pose(rng)
+    xi = np.array(helpers.CONFIG1_TWIST)
+    T_end = T_start @ oracle.se3_exp(xi)
+    p = capi.frame_params_from_poses(T_start, T_end, 0.0, 0.1, 0.05)
+    out = run_frame(cuda, capi, pts, p)
+    ref = oracle.deskew_xyzi_scan(pts, T_start, T_end, 0.0, 0.1, 0.05, allow_abort=True)
+    assert np.array_equal(np.isfinite(out[:, :3]), np.isfinite(ref[:, :3]))
+    good = np.isfinite(ref[:, :3]).all(axis=1)
+    assert np.abs(out[good, :3] - ref[good, :3]).max() < TOL_M
+
+
+# ---- batches ------------------------------------------------------------------------------------------------------
+def make_batch(oracle, sizes, seed, mercator=False):
+    rng = np.random.default_rng(seed)
+    scans, frames = [], []
+    for k, n in enumerate(sizes):
+        scans.append(helpers.synthetic_scan(n, 64, seed + k) if n else np.zeros((0, 4), np.float32))
+        T_start = helpers.random_pose(rng, mercator)
+        xi = helpers.random_twist(rng)
+        frames.append((T_start, T_start @ oracle.se3_exp(xi), xi, rng.uniform(0, 1)))
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return np.concatenate(scans), offsets, frames
+
+
+def batch_params(capi, frames, t0=10.0, t2=10.1):
+    return capi.params_array([capi.frame_params_from_poses(Ts, Te, t0, t2, t0 + xr * (t2 - t0)) for Ts, Te, _, xr in frames])
+
+
+def test_batch_ragged_frames_match_oracle(capi, oracle, cuda):
+    """Ragged batch incl. empty frames, 1-point frames, odd offsets (frame starts that are not 32-byte aligned) and
+    frames larger than a work item."""
+    sizes = [1000, 0, 1, 3, 2047, 2048, 2049, 0, 0, 5, 30_001, 17, 70_000, 2, 9_999]
+    pts, offsets, frames = make_batch(oracle, sizes, 100, mercator=True)
+    params = batch_params(capi, frames)
+    out = run_batch(cuda, capi, pts, offsets, params)
+    assert np.array_equal(out[:, 3], pts[:, 3])
+    for f, (Ts, Te, xi, xr) in enumerate(frames):
+        a, b = offsets[f], offsets[f + 1]
+        if a == b:
+            continue
+        sl = slice(a, b, 5) if b - a > 5000 else slice(a, b)
+        ref = oracle.deskew_xyzi_scan(pts[sl], Ts, Te, 10.0, 10.1, 10.0 + xr * 0.1)
+        assert helpers.max_abs_err(out[sl], ref) < TOL_M, f"frame {f}"
+        cf = helpers.closed_form_deskew(pts[a:b], xi, xr)
+        assert np.abs(out[a:b, :3] - cf).max() < TOL_M, f"frame {f}"
+
+
+def test_batch_equals_frame_by_frame_bitwise(capi, oracle, cuda):
+    """A frame's result must not depend on its batch neighbours, its position or the launch shape (SURVEY 4 iv)."""
+    sizes = [130_000] * 6 + [64_321, 130_000]
+    pts, offsets, frames = make_batch(oracle, sizes, 200)
+    params = batch_params(capi, frames)
+    out = run_batch(cuda, capi, pts, offsets, params)
+    for f in range(len(sizes)):
+        a, b = offsets[f], offsets[f + 1]
+        p = capi.FrameParams.from_buffer_copy(params[f:f + 1].tobytes())
+        single = run_frame(cuda, capi, pts[a:b], p)
+        assert single.tobytes() == out[a:b].tobytes(), f"frame {f}"
+
+
+def test_batch_launch_shapes_agree_bitwise(capi, oracle, cuda, monkeypatch):
+    """Every (vec, unroll, hint, ctas, item_tiles) shape computes the same bits."""
+    sizes = [130_000, 99_999, 130_001, 4_097, 130_000]
+    pts, offsets, frames = make_batch(oracle, sizes, 300)
+    params = batch_params(capi, frames)
+    monkeypatch.delenv("KMC_B200_TUNE", raising=False)
+    want = run_batch(cuda, capi, pts, offsets, params)
+    for tune in ["vec=1,unroll=1,hint=0,ctas=1,item_tiles=1", "vec=1,unroll=4,hint=2,ctas=8,item_tiles=3",
+                 "vec=2,unroll=1,hint=1,ctas=2,item_tiles=64", "vec=2,unroll=4,hint=0,ctas=4,item_tiles=8",
+                 "vec=2,unroll=2,hint=2,ctas=6,item_tiles=1000"]:
+        monkeypatch.setenv("KMC_B200_TUNE", tune)
+        got = run_batch(cuda, capi, pts, offsets, params)
+        assert got.tobytes() == want.tobytes(), tune
+
+
+def test_sharding_is_invisible(capi, oracle, cuda):
+    """Splitting the batch into G contiguous frame ranges (what each GPU of a box receives) reproduces the 1-GPU bits."""
+    sizes = [20_000 + 111 * k for k in range(13)]
+    pts, offsets, frames = make_batch(oracle, sizes, 400)
+    params = batch_params(capi, frames)
+    want = run_batch(cuda, capi, pts, offsets, params)
+    for g in (2, 4, 8):
+        parts = []
+        for i in range(g):
+            fb, fe = capi.shard_range(len(sizes), g, i)
+            if fe == fb:
+                continue
+            local = offsets[fb:fe + 1] - offsets[fb]
+            parts.append(run_batch(cuda, capi, pts[offsets[fb]:offsets[fe]], local, params[fb:fe]))
+        assert np.concatenate(parts).tobytes() == want.tobytes(), f"G={g}"
+
+
+# ---- host entry points (H2D + kernel + D2H inside the call) ---------------------------------------------------------------
+def test_host_frame_and_batch_calls(capi, oracle, cuda):
+    sizes = [130_000, 1, 77_777, 0, 130_000, 250_001]
+    pts, offsets, frames = make_batch(oracle, sizes, 500)
+    params = batch_params(capi, frames)
+    want = run_batch(cuda, capi, pts, offsets, params)
+    with capi.Handle(0, 100_000) as h:  # capacity smaller than the frames: chunks cut frames
+        assert h.device == 0 and h.capacity >= 100_000
+        got = h.deskew_batch(pts, offsets, params)
+        assert got.tobytes() == want.tobytes()
+        a, b = offsets[5], offsets[6]
+        p = capi.FrameParams.from_buffer_copy(params[5:6].tobytes())
+        one = h.deskew_frame(pts[a:b], p)
+        assert one.tobytes() == want[a:b].tobytes()
+        # pinned host memory takes the zero-staging path
+        torch = cuda
+        pin_in = torch.from_numpy(pts).pin_memory()
+        pin_out = torch.empty_like(pin_in).pin_memory()
+        h.deskew_batch_ptr(pin_in.data_ptr(), pin_out.data_ptr(), offsets, params)
+        assert pin_out.numpy().tobytes() == want.tobytes()
+
+
+def test_multi_gpu_entry_point_with_available_devices(capi, oracle, cuda):
+    """kmc_b200_deskew_batch_multi_gpu over however many devices the box has (1 on the test box: degenerates to one shard)."""
+    n_dev = min(capi.lib().kmc_b200_device_count(), 8)
+    sizes = [30_000 + 7 * k for k in range(11)]
+    pts, offsets, frames = make_batch(oracle, sizes, 600)
+    params = batch_params(capi, frames)
+    want = run_batch(cuda, capi, pts, offsets, params)
+    handles = [capi.Handle(d, 50_000) for d in range(n_dev)]
+    try:
+        got = capi.deskew_batch_multi_gpu(handles, pts, offsets, params)
+    finally:
+        for h in handles:
+            h.close()
+    assert got.tobytes() == want.tobytes()
+
+
+def test_kitti_bin_file_roundtrip(capi, oracle, cuda, tmp_path):
+    """KittiPclLoader::LoadPointcloud + MotionCompensateFrame + WritePointcloud (data_io.cpp:101-138, 287-313) as one call."""
+    src = os.path.join(helpers.GOLDEN, "kitti_2011_09_26_drive_0005_frame0.bin")
+    dst = str(tmp_path / "0000000000.bin")
+    T_start, T_end, t0, t1, t2 = helpers.config1_frame()
+    p = capi.frame_params_from_poses(T_start, T_end, t0, t2, t1)
+    with capi.Handle(0, 250_000) as h:
+        n = h.deskew_bin_file(src, dst, p)
+        assert n == 123_397
+        with pytest.raises(capi.KmcError) as e:
+            h.deskew_bin_file(str(tmp_path / "missing.bin"), dst, p)
+        assert e.value.status == capi.ERR_IO
+    out = np.fromfile(dst, dtype=np.float32).reshape(-1, 4)
+    pts = helpers.real_scan()
+    ref = oracle.deskew_xyzi_scan(pts[::9], T_start, T_end, t0, t2, t1)
+    assert helpers.max_abs_err(out[::9], ref) < TOL_M
+    assert np.array_equal(out[:, 3], pts[:, 3])  # WritePointcloud writes the untouched intensities (data_io.cpp:308)
+
+
+def test_pseudo_time_stamps_device(capi, oracle, cuda):
+    """GetPseudoTimeStamps (timestamp_mocking.cpp:56-63) on the device, double precision."""
+    torch = cuda
+    pts = np.concatenate([helpers.edge_points(), helpers.real_scan()[:50_000]])
+    t0, t2 = 47072.283701593, 47072.386973931
+    d_in = dev(torch, pts)
+    d_out = torch.empty(pts.shape[0], dtype=torch.float64, device="cuda")
+    capi.pseudo_time_stamps_device(d_in.data_ptr(), d_out.data_ptr(), pts.shape[0], t0, t2, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    cloud = np.concatenate([pts[:, :3].astype(np.float64), np.ones((len(pts), 1))], axis=1)
+    want = oracle.pseudo_time_stamps(cloud, t0, t2)
+    assert np.abs(got - want).max() < 1e-10  # seconds; the stamps are ~4.7e4 s so 1 ulp is 7e-12
+    assert got[0] == t0 + 1.0 * (t2 - t0) and got[1] == t0  # frac exactly 1 and 0
+
+
+# ---- full-size properties (BASELINE configs 3 and 5), no oracle needed ---------------------------------------------------
+def test_synthetic_generator_is_seeded_and_shard_independent(capi, cuda):
+    torch = cuda
+    n, scans = 130_000, 6
+    a = torch.empty((scans * n, 4), dtype=torch.float32, device="cuda")
+    b = torch.empty((2 * n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(a.data_ptr(), n, scans, 64, 20110926, 0)
+    capi.synth_scans_device(b.data_ptr(), n, 2, 64, 20110926, 4)  # scans 4 and 5 generated on "another GPU"
+    torch.cuda.synchronize()
+    assert torch.equal(a[4 * n:], b)
+    assert not torch.equal(a[:n], a[n:2 * n])
+    pts = a[:n].cpu().numpy()
+    r = np.linalg.norm(pts[:, :3], axis=1)
+    assert r.min() >= 1.99 and r.max() < 120.1 and pts[:, 3].min() >= 0 and pts[:, 3].max() <= 0.99
+    az = np.arctan2(pts[:, 1], pts[:, 0])
+    assert np.histogram(az, bins=8, range=(-np.pi, np.pi))[0].min() > n / 16  # all the way round
+
+
+def test_large_batch_properties_and_spot_parity(capi, oracle, cuda):
+    """A bandwidth-sized batch (2 000 x 130 000 points = 8.3 GB of traffic; the bench runs the full 10 000):
+    identity twist frames come back bit-exact, w passes through, applying xi then -xi with the fraction carried in w
+    returns the input (round trip), and sampled frames match the oracle."""
+    torch = cuda
+    n, scans = 130_000, 2_000
+    params, xi = capi.synth_frame_params(scans, 20110926, 0, 0.5)
+    zero_frames = [0, 777, scans - 1]
+    for f in zero_frames:
+        params[f:f + 1] = capi.params_array([capi.frame_params_from_twist([0] * 6, 0.5)])
+    d_in = torch.empty((scans * n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(d_in.data_ptr(), n, scans, 64, 20110926, 0)
+    d_out = torch.empty_like(d_in)
+    d_off = torch.arange(0, (scans + 1) * n, n, dtype=torch.int64, device="cuda")
+    d_par = dev(torch, params.view(np.uint8))
+    stream = torch.cuda.current_stream().cuda_stream
+    capi.deskew_batch_device(d_in.data_ptr(), d_out.data_ptr(), d_off.data_ptr(), d_par.data_ptr(), scans, scans * n, 0, stream)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out[:, 3], d_in[:, 3])
+    for f in zero_frames:
+        assert torch.equal(d_out[f * n:(f + 1) * n], d_in[f * n:(f + 1) * n])
+    moved = (d_out[:, :3] - d_in[:, :3]).abs().amax(dim=1)
+    assert float(moved.max()) < 12.0 and float(moved[n:2 * n].max()) > 1e-3
+    for f in (1, 1234, scans - 2):
+        pts = d_in[f * n:(f + 1) * n:16].cpu().numpy()
+        got = d_out[f * n:(f + 1) * n:16].cpu().numpy()
+        T_end = oracle.se3_exp(xi[f])
+        ref = oracle.deskew_xyzi_scan(pts, np.eye(4), T_end, 0.0, 0.1, 0.05)
+        assert helpers.max_abs_err(got, ref) < TOL_M, f"frame {f}"
+    # round trip in FROM_W mode: out = Exp(s xi) p, back = Exp(-s xi) out, with the same s = w - 0.5 in the w lane
+    del d_out
+    az = torch.atan2(d_in[:, 1].double(), d_in[:, 0].double())
+    d_in[:, 3] = ((np.pi - az) / (2 * np.pi)).float()
+    del az
+    fwd = torch.empty_like(d_in)
+    capi.deskew_batch_device(d_in.data_ptr(), fwd.data_ptr(), d_off.data_ptr(), d_par.data_ptr(), scans, scans * n, 1, stream)
+    neg = capi.params_array([capi.frame_params_from_twist(-xi[f] if f not in zero_frames else [0] * 6, 0.5) for f in range(scans)])
+    d_neg = dev(torch, neg.view(np.uint8))
+    capi.deskew_batch_device(fwd.data_ptr(), fwd.data_ptr(), d_off.data_ptr(), d_neg.data_ptr(), scans, scans * n, 1, stream)
+    torch.cuda.synchronize()
+    assert float((fwd[:, :3] - d_in[:, :3]).abs().max()) < 3e-5  # two float32 roundings at up to 120 m + 2 x 1e-7 x |displacement|
+
+
+def test_config5_dense_10m_point_frame(capi, oracle, cuda):
+    """BASELINE config 5: one dense 128-beam frame of 10 M points; parity on a 1-in-4000 sample + closed form on 1 %."""
+    torch = cuda
+    n = 10_000_000
+    d_in = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(d_in.data_ptr(), n, 1, 128, 20110926, 0)
+    xi = np.array([2.1, -0.04, 0.02, 0.002, -0.005, 0.06])
+    T_start = helpers.random_pose(np.random.default_rng(8), mercator=True)
+    T_end = T_start @ oracle.se3_exp(xi)
+    p = capi.frame_params_from_poses(T_start, T_end, 0.0, 0.1, 0.05)
+    d_out = torch.empty_like(d_in)
+    capi.deskew_frame_device(d_in.data_ptr(), d_out.data_ptr(), n, p, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out[:, 3], d_in[:, 3])
+    pts, got = d_in[::4000].cpu().numpy(), d_out[::4000].cpu().numpy()
+    ref = oracle.deskew_xyzi_scan(pts, T_start, T_end, 0.0, 0.1, 0.05)
+    assert helpers.max_abs_err(got, ref) < TOL_M
+    pts, got = d_in[::100].cpu().numpy(), d_out[::100].cpu().numpy()
+    assert np.abs(got[:, :3] - helpers.closed_form_deskew(pts, xi, 0.5)).max() < TOL_M
+    # the last points of the frame (tail tiles) are written
+    tail_in, tail_out = d_in[-3000:].cpu().numpy(), d_out[-3000:].cpu().numpy()
+    assert np.abs(tail_out[:, :3] - helpers.closed_form_deskew(tail_in, xi, 0.5)).max() < TOL_M

@@ -387,7 +387,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "scans_per_gpu": my_scans, "points_per_scan": points,
                        "points_per_step_all_gpus": int(all_pts), "bytes_per_point": BYTES_PER_POINT, "seed": SEED,
-                       "l2": "inputs (20.8 GB in + 20.8 GB out per GPU) far exceed the 126 MB L2; no flush needed",
+                       "l2": f"inputs ({n_pts * 16 / 1e9:.1f} GB in + {n_pts * 16 / 1e9:.1f} GB out per GPU) far exceed the 126 MB L2; no flush between steps needed",
                        "timing": "CUDA events on the launching stream, barrier+synchronize both sides, max over ranks",
                        "parallelism": f"frame-sharded x{world}, no collective", "shrunk_to_fit": shrunk,
                        "tune": os.environ.get("KMC_B200_TUNE", "default")},

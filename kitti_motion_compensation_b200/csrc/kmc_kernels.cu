@@ -208,7 +208,7 @@ __device__ __forceinline__ float4 DeskewPoint(float4 p, const kmc_b200_frame_par
 // ---------------------------------------------------------------------------------------------------------------
 // A contiguous range [a, b) of points that all belong to one frame, processed by the whole CTA.
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE, int VEC, int UNROLL, int HINT>
+template <int MODE, int VEC, int UNROLL, int HINT, int BLOCK>
 __device__ __forceinline__ void ProcessRange(const float4* __restrict__ in, float4* __restrict__ out, int64_t a, int64_t b,
                                              const kmc_b200_frame_params& P) {
   int const tid = threadIdx.x;
@@ -218,43 +218,43 @@ __device__ __forceinline__ void ProcessRange(const float4* __restrict__ in, floa
       a += 1;
     }
   }
-  constexpr int64_t kTile = static_cast<int64_t>(kBlockThreads) * UNROLL * VEC;
+  constexpr int64_t kTile = static_cast<int64_t>(BLOCK) * UNROLL * VEC;
   int64_t base = a;
   for (; base + kTile <= b; base += kTile) {
     if constexpr (VEC == 2) {
       Point2 v[UNROLL];
 #pragma unroll
-      for (int j = 0; j < UNROLL; ++j) v[j] = LoadPoint2<HINT>(in + base + 2 * (j * kBlockThreads + tid));
+      for (int j = 0; j < UNROLL; ++j) v[j] = LoadPoint2<HINT>(in + base + 2 * (j * BLOCK + tid));
 #pragma unroll
       for (int j = 0; j < UNROLL; ++j) {
         Point2 r;
         r.a = DeskewPoint<MODE>(v[j].a, P);
         r.b = DeskewPoint<MODE>(v[j].b, P);
-        StorePoint2<HINT>(out + base + 2 * (j * kBlockThreads + tid), r);
+        StorePoint2<HINT>(out + base + 2 * (j * BLOCK + tid), r);
       }
     } else {
       float4 v[UNROLL];
 #pragma unroll
-      for (int j = 0; j < UNROLL; ++j) v[j] = LoadPoint<HINT>(in + base + j * kBlockThreads + tid);
+      for (int j = 0; j < UNROLL; ++j) v[j] = LoadPoint<HINT>(in + base + j * BLOCK + tid);
 #pragma unroll
-      for (int j = 0; j < UNROLL; ++j) StorePoint<HINT>(out + base + j * kBlockThreads + tid, DeskewPoint<MODE>(v[j], P));
+      for (int j = 0; j < UNROLL; ++j) StorePoint<HINT>(out + base + j * BLOCK + tid, DeskewPoint<MODE>(v[j], P));
     }
   }
-  for (int64_t i = base + tid; i < b; i += kBlockThreads) StorePoint<HINT>(out + i, DeskewPoint<MODE>(LoadPoint<HINT>(in + i), P));
+  for (int64_t i = base + tid; i < b; i += BLOCK) StorePoint<HINT>(out + i, DeskewPoint<MODE>(LoadPoint<HINT>(in + i), P));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // single frame: per-frame constants as a __grid_constant__ parameter (constant bank, broadcast to every lane for free)
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE, int VEC, int UNROLL, int HINT>
-__global__ void __launch_bounds__(kBlockThreads)
+template <int MODE, int VEC, int UNROLL, int HINT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
     DeskewFrameKernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t n, int64_t item_points,
                       const __grid_constant__ kmc_b200_frame_params P) {
   int64_t const n_items = (n + item_points - 1) / item_points;
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     int64_t const p0 = item * item_points;
     int64_t const p1 = (p0 + item_points < n) ? (p0 + item_points) : n;
-    ProcessRange<MODE, VEC, UNROLL, HINT>(in, out, p0, p1, P);
+    ProcessRange<MODE, VEC, UNROLL, HINT, BLOCK>(in, out, p0, p1, P);
   }
 }
 
@@ -288,8 +288,8 @@ __device__ __forceinline__ int LocateFrame(const int64_t* __restrict__ offsets, 
   return lo;
 }
 
-template <int MODE, int VEC, int UNROLL, int HINT>
-__global__ void __launch_bounds__(kBlockThreads)
+template <int MODE, int VEC, int UNROLL, int HINT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
     DeskewBatchKernel(const float4* __restrict__ in, float4* __restrict__ out, const int64_t* __restrict__ offsets,
                       const kmc_b200_frame_params* __restrict__ table, int n_frames, int64_t n, int64_t item_points,
                       int64_t point_base, double frames_per_point) {
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kBlockThreads)
       }
       int64_t const seg_end = frame_end < p1 ? frame_end : p1;
       kmc_b200_frame_params const P = LoadParamsWarpBroadcast(table, f);
-      ProcessRange<MODE, VEC, UNROLL, HINT>(in, out, p0, seg_end, P);
+      ProcessRange<MODE, VEC, UNROLL, HINT, BLOCK>(in, out, p0, seg_end, P);
       p0 = seg_end;
       ++f;
     }
@@ -368,75 +368,83 @@ __global__ void __launch_bounds__(kBlockThreads)
 // ---------------------------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE, int VEC, int UNROLL, int HINT>
+template <int MODE, int VEC, int UNROLL, int HINT, int BLOCK>
 cudaError_t LaunchFrameT(const float* in, float* out, int64_t n, const kmc_b200_frame_params& P, const LaunchConfig& cfg,
                          int sm_count, cudaStream_t stream) {
-  int64_t const tile = static_cast<int64_t>(kBlockThreads) * UNROLL * VEC;
+  int64_t const tile = static_cast<int64_t>(BLOCK) * UNROLL * VEC;
   int64_t const item_points = tile * cfg.item_tiles;
   int64_t const n_items = (n + item_points - 1) / item_points;
-  int64_t grid = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm;
+  int64_t grid = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm;  // CTAs resident per SM, whatever their size
   if (grid > n_items) grid = n_items;
   if (grid < 1) grid = 1;
-  DeskewFrameKernel<MODE, VEC, UNROLL, HINT><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(
+  DeskewFrameKernel<MODE, VEC, UNROLL, HINT, BLOCK><<<static_cast<unsigned>(grid), BLOCK, 0, stream>>>(
       reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), n, item_points, P);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
 
-template <int MODE, int VEC, int UNROLL, int HINT>
+template <int MODE, int VEC, int UNROLL, int HINT, int BLOCK>
 cudaError_t LaunchBatchT(const float* in, float* out, const int64_t* offsets, const kmc_b200_frame_params* table,
                          int32_t n_frames, int64_t n, int64_t point_base, int64_t n_batch_points, const LaunchConfig& cfg,
                          int sm_count, cudaStream_t stream) {
-  int64_t const tile = static_cast<int64_t>(kBlockThreads) * UNROLL * VEC;
+  int64_t const tile = static_cast<int64_t>(BLOCK) * UNROLL * VEC;
   int64_t const item_points = tile * cfg.item_tiles;
   int64_t const n_items = (n + item_points - 1) / item_points;
-  int64_t grid = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm;
+  int64_t grid = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm;  // CTAs resident per SM, whatever their size
   if (grid > n_items) grid = n_items;
   if (grid < 1) grid = 1;
   double const frames_per_point = static_cast<double>(n_frames) / static_cast<double>(n_batch_points);
-  DeskewBatchKernel<MODE, VEC, UNROLL, HINT><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(
+  DeskewBatchKernel<MODE, VEC, UNROLL, HINT, BLOCK><<<static_cast<unsigned>(grid), BLOCK, 0, stream>>>(
       reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), offsets, table, n_frames, n, item_points,
       point_base, frames_per_point);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
 
+// Expands the runtime knobs into template instantiations.  (vec, unroll) in {1,2}x{1,2}, hint in {0,1}, block in {128,256,512}.
+template <int MODE, int V, int U, int H>
+cudaError_t DispatchFrameBlock(const float* in, float* out, int64_t n, const kmc_b200_frame_params& P, const LaunchConfig& cfg,
+                               int sm, cudaStream_t st) {
+  if (cfg.block == 128) return LaunchFrameT<MODE, V, U, H, 128>(in, out, n, P, cfg, sm, st);
+  if (cfg.block == 512) return LaunchFrameT<MODE, V, U, H, 512>(in, out, n, P, cfg, sm, st);
+  return LaunchFrameT<MODE, V, U, H, 256>(in, out, n, P, cfg, sm, st);
+}
+
 template <int MODE>
 cudaError_t DispatchFrame(const float* in, float* out, int64_t n, const kmc_b200_frame_params& P, const LaunchConfig& cfg,
                           int sm, cudaStream_t st) {
-#define KMC_FRAME_CALL(V, U)                                                        \
-  switch (cfg.hint) {                                                               \
-    case 0: return LaunchFrameT<MODE, V, U, 0>(in, out, n, P, cfg, sm, st);         \
-    case 1: return LaunchFrameT<MODE, V, U, 1>(in, out, n, P, cfg, sm, st);         \
-    default: return LaunchFrameT<MODE, V, U, 2>(in, out, n, P, cfg, sm, st);        \
-  }
+#define KMC_FRAME_CALL(V, U)                                                                          \
+  return cfg.hint ? DispatchFrameBlock<MODE, V, U, 1>(in, out, n, P, cfg, sm, st)                     \
+                  : DispatchFrameBlock<MODE, V, U, 0>(in, out, n, P, cfg, sm, st);
   if (cfg.vec == 2) {
-    if (cfg.unroll >= 4) { KMC_FRAME_CALL(2, 4) }
     if (cfg.unroll >= 2) { KMC_FRAME_CALL(2, 2) }
     KMC_FRAME_CALL(2, 1)
   }
-  if (cfg.unroll >= 4) { KMC_FRAME_CALL(1, 4) }
   if (cfg.unroll >= 2) { KMC_FRAME_CALL(1, 2) }
   KMC_FRAME_CALL(1, 1)
 #undef KMC_FRAME_CALL
+}
+
+template <int MODE, int V, int U, int H>
+cudaError_t DispatchBatchBlock(const float* in, float* out, const int64_t* offsets, const kmc_b200_frame_params* table,
+                               int32_t n_frames, int64_t n, int64_t base, int64_t nb, const LaunchConfig& cfg, int sm,
+                               cudaStream_t st) {
+  if (cfg.block == 128) return LaunchBatchT<MODE, V, U, H, 128>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);
+  if (cfg.block == 512) return LaunchBatchT<MODE, V, U, H, 512>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);
+  return LaunchBatchT<MODE, V, U, H, 256>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);
 }
 
 template <int MODE>
 cudaError_t DispatchBatch(const float* in, float* out, const int64_t* offsets, const kmc_b200_frame_params* table,
                           int32_t n_frames, int64_t n, int64_t base, int64_t nb, const LaunchConfig& cfg, int sm,
                           cudaStream_t st) {
-#define KMC_BATCH_CALL(V, U)                                                                          \
-  switch (cfg.hint) {                                                                                 \
-    case 0: return LaunchBatchT<MODE, V, U, 0>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);    \
-    case 1: return LaunchBatchT<MODE, V, U, 1>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);    \
-    default: return LaunchBatchT<MODE, V, U, 2>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);   \
-  }
+#define KMC_BATCH_CALL(V, U)                                                                                              \
+  return cfg.hint ? DispatchBatchBlock<MODE, V, U, 1>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st)         \
+                  : DispatchBatchBlock<MODE, V, U, 0>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);
   if (cfg.vec == 2) {
-    if (cfg.unroll >= 4) { KMC_BATCH_CALL(2, 4) }
     if (cfg.unroll >= 2) { KMC_BATCH_CALL(2, 2) }
     KMC_BATCH_CALL(2, 1)
   }
-  if (cfg.unroll >= 4) { KMC_BATCH_CALL(1, 4) }
   if (cfg.unroll >= 2) { KMC_BATCH_CALL(1, 2) }
   KMC_BATCH_CALL(1, 1)
 #undef KMC_BATCH_CALL
@@ -458,6 +466,7 @@ void ApplyTuneEnv(LaunchConfig& cfg) {
     else if (!std::strcmp(tok, "hint")) cfg.hint = v;
     else if (!std::strcmp(tok, "ctas")) cfg.ctas_per_sm = v;
     else if (!std::strcmp(tok, "item_tiles")) cfg.item_tiles = v;
+    else if (!std::strcmp(tok, "block")) cfg.block = v;
   }
 }
 
@@ -466,30 +475,34 @@ void ApplyTuneEnv(LaunchConfig& cfg) {
 uint64_t LaunchCount() { return g_launches.load(std::memory_order_relaxed); }
 
 LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_count) {
+  // Defaults from the B200 sweeps (profiles/sweep_r01*.json): one 256-bit load + one 256-bit store per thread per tile,
+  // plain ld/st, 4 CTAs x 256 threads per SM (32 KB of loads in flight per SM).  More bytes in flight per thread or more
+  // resident CTAs measured SLOWER (5.9 vs 6.5 TB/s): the kernel is at the copy ceiling and extra requests only lengthen
+  // the DRAM queues.
   LaunchConfig cfg;
   cfg.vec = 2;
-  cfg.unroll = 2;
-  cfg.hint = 1;
+  cfg.unroll = 1;
+  cfg.hint = 0;
+  cfg.block = 256;
   cfg.ctas_per_sm = 4;
-  cfg.item_tiles = 8;
-  // Small inputs are latency bound: spread them over as many CTAs as possible instead of deep per-thread unrolling.
-  int64_t const big = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm * kBlockThreads * cfg.unroll * cfg.vec * cfg.item_tiles;
-  if (n_points < big) {
-    cfg.item_tiles = 1;
-    int64_t const mid = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm * kBlockThreads * cfg.unroll * cfg.vec;
-    if (n_points < mid) {
-      cfg.vec = 1;
-      cfg.unroll = 1;
-    }
+  cfg.item_tiles = 16;
+  // Small inputs are latency bound: spread them over as many CTAs as possible.
+  int64_t const tile = static_cast<int64_t>(cfg.block) * cfg.unroll * cfg.vec;
+  int64_t const resident = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm;
+  if (n_points < resident * tile * cfg.item_tiles * 4) {
+    int64_t const per_cta_tiles = n_points / (resident * tile);
+    cfg.item_tiles = per_cta_tiles >= 8 ? 4 : 1;
+    if (n_points < resident * tile) cfg.vec = 1;
   }
   ApplyTuneEnv(cfg);
   if (!aligned32) cfg.vec = 1;
-  if (in_place) cfg.hint = 0;  // the .nc path assumes the input is read-only for the whole kernel
+  if (in_place && cfg.hint == 1) cfg.hint = 0;  // the .nc path assumes the input is read-only for the whole kernel
   if (cfg.vec != 2) cfg.vec = 1;
   if (cfg.unroll < 1) cfg.unroll = 1;
-  if (cfg.hint < 0 || cfg.hint > 2) cfg.hint = 1;
+  if (cfg.hint < 0 || cfg.hint > 1) cfg.hint = 0;
+  if (cfg.block != 128 && cfg.block != 512) cfg.block = 256;
   if (cfg.ctas_per_sm < 1) cfg.ctas_per_sm = 1;
-  if (cfg.ctas_per_sm > 8) cfg.ctas_per_sm = 8;
+  if (cfg.ctas_per_sm > 16) cfg.ctas_per_sm = 16;
   if (cfg.item_tiles < 1) cfg.item_tiles = 1;
   return cfg;
 }

@@ -9,11 +9,12 @@
 namespace kmc_b200::dev {
 
 // Kernel shape knobs.  Defaults are chosen by PickConfig(); a sweep (tools/sweep.py) can override them through the
-// KMC_B200_TUNE environment variable ("vec=2,unroll=4,hint=1,ctas=4,item_tiles=8") without recompiling.
+// KMC_B200_TUNE environment variable ("vec=2,unroll=1,hint=0,block=256,ctas=4,item_tiles=16") without recompiling.
 struct LaunchConfig {
   int vec;         // points per memory instruction: 1 = 128-bit LDG/STG, 2 = 256-bit LDG/STG (sm_100 only)
-  int unroll;      // memory instructions in flight per thread per tile (1, 2, 4)
-  int hint;        // 0 = plain ld/st, 1 = L1::no_allocate (+ .nc load), 2 = .cs streaming (evict-first)
+  int unroll;      // memory instructions in flight per thread per tile (1, 2)
+  int hint;        // 0 = plain ld/st, 1 = L1::no_allocate (+ .nc load)
+  int block;       // threads per CTA (128, 256, 512)
   int ctas_per_sm; // persistent grid = SMs * ctas_per_sm (capped by the number of work items)
   int item_tiles;  // tiles per work item (a work item is the unit a CTA takes per scheduling step)
 };

@@ -126,6 +126,10 @@ KMC_B200_API int kmc_b200_relative_pose_between_times(double t1, const double P1
 KMC_B200_API double kmc_b200_fraction_of_scan_completed(double x, double y);
 KMC_B200_API double kmc_b200_pseudo_time_stamp(double x, double y, double scan_start, double scan_end);
 
+/* OxtsToPose (data_io.cpp:68-88): Mercator position (scale * R_earth * ...) and Rz(yaw) Ry(pitch) Rx(roll). */
+KMC_B200_API int kmc_b200_oxts_to_pose(double lat, double lon, double alt, double roll, double pitch, double yaw, double scale,
+                                       double T_colmajor[16]);
+
 /* Contiguous split of n_items over n_parts (frame sharding across GPUs): part `index` owns [*begin, *end). */
 KMC_B200_API int kmc_b200_shard_range(int64_t n_items, int32_t n_parts, int32_t index, int64_t* begin, int64_t* end);
 
@@ -144,6 +148,10 @@ KMC_B200_API int kmc_b200_deskew_batch_device(const float* xyzi_in, float* xyzi_
  * start + frac(x_i, y_i) * (end - start). */
 KMC_B200_API int kmc_b200_pseudo_time_stamps_device(const float* xyzi_in, double* stamps_out, int64_t n_points, double scan_start,
                                        double scan_end, void* stream);
+/* The same on the reference's own cloud layout: x and y are the first two COLUMNS of the column-major N x 4 double
+ * matrix (Pointcloud::data() and data() + N), device pointers. */
+KMC_B200_API int kmc_b200_pseudo_time_stamps_xy_device(const double* x, const double* y, double* stamps_out, int64_t n_points,
+                                                       double scan_start, double scan_end, void* stream);
 /* Seeded synthetic HDL-64E style scans written straight into device memory (benchmark input):
  * n_scans scans of points_per_scan points, scan k uses seed + first_scan_index + k, so a scan's content does not
  * depend on which GPU generates it.  n_rings x azimuth steps, ring-major, log-uniform range in [2, 120) m. */
@@ -158,6 +166,9 @@ KMC_B200_API int kmc_b200_synth_frame_params(int32_t n_frames, uint64_t seed, in
 /* capacity_points: largest single transfer chunk the handle can stage (reference loader: 250 000, data_io.hpp:17). */
 KMC_B200_API int kmc_b200_handle_create(int device, int64_t capacity_points, kmc_b200_handle** out);
 KMC_B200_API int kmc_b200_handle_destroy(kmc_b200_handle* h);
+/* Process-wide handle of a device, created on first use with the reference loader's capacity (250 000 points) and owned
+ * by the library (do not destroy).  Used by the C++ mirror, whose reference signatures carry no handle. */
+KMC_B200_API int kmc_b200_default_handle(int device, kmc_b200_handle** out);
 KMC_B200_API int kmc_b200_handle_device(const kmc_b200_handle* h);
 KMC_B200_API int64_t kmc_b200_handle_capacity(const kmc_b200_handle* h);
 
@@ -174,6 +185,9 @@ KMC_B200_API int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* xyz
 KMC_B200_API int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_handles, const float* xyzi_in,
                                     float* xyzi_out, const int64_t* frame_offsets, const kmc_b200_frame_params* params,
                                     int32_t n_frames, int time_mode);
+/* GetPseudoTimeStamps on host columns x, y (length n each): H2D + kernel + D2H. */
+KMC_B200_API int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n_points,
+                                                     double scan_start, double scan_end, double* stamps_out);
 /* KITTI .bin in, deskewed .bin out (KittiPclLoader::LoadPointcloud + MotionCompensateFrame + WritePointcloud,
  * data_io.cpp:101-138, 287-313) without the float->double->float round trip.  n_points_out may be NULL. */
 KMC_B200_API int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out,

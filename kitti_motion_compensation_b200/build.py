@@ -56,5 +56,45 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+DROPIN_HEADERS = ["data_types.hpp", "eigen_shim.hpp", "lie_algebra.hpp", "trajectory_interpolation.hpp", "timestamp_mocking.hpp",
+                  "motion_compensation.hpp", "data_io.hpp", "handlers.hpp", "utils.hpp", "data_handle.hpp"]
+
+
+def _cxx() -> str:
+    return os.environ.get("CXX") or shutil.which("g++") or "g++"
+
+
+def build_dropin(force: bool = False) -> str:
+    """libkitti_motion_compensation_lib.so — the C++ mirror of the reference API (reference CMakeLists.txt:27-29 names
+    its library the same), linked against libkmc_b200.so next to it."""
+    build(force=force)
+    src = os.path.join(CSRC, "kmc_dropin.cpp")
+    inc = os.path.join(REPO_DIR, "include")
+    deps = [src, os.path.join(inc, "kmc_b200.h"), os.path.abspath(__file__)]
+    deps += [os.path.join(inc, "kitti_motion_compensation", h) for h in DROPIN_HEADERS]
+    if not force and not _stale(DROPIN_LIB_PATH, deps):
+        return DROPIN_LIB_PATH
+    cmd = [_cxx(), "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-I", inc, "-o", DROPIN_LIB_PATH, src,
+           "-L", LIB_DIR, "-lkmc_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return DROPIN_LIB_PATH
+
+
+def build_cpp_test(name: str, force: bool = False) -> str:
+    """Compiles tests/cpp/<name>.cpp against the drop-in library; returns the binary path (tests/cpp/_build/<name>)."""
+    build_dropin()
+    tests = os.path.join(REPO_DIR, "tests", "cpp")
+    out_dir = os.path.join(tests, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    src, out = os.path.join(tests, name + ".cpp"), os.path.join(out_dir, name)
+    if not force and not _stale(out, [src, os.path.join(tests, "mini_gtest.hpp"), DROPIN_LIB_PATH]):
+        return out
+    cmd = [_cxx(), "-std=c++17", "-O1", "-Wall", "-I", os.path.join(REPO_DIR, "include"), "-I", tests, "-o", out, src,
+           "-L", LIB_DIR, "-lkitti_motion_compensation_lib", "-lkmc_b200", f"-Wl,-rpath,{LIB_DIR}"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_dropin(force="--force" in sys.argv))

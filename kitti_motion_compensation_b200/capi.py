@@ -76,19 +76,23 @@ SIGNATURES = {
     "kmc_b200_relative_pose_between_times": (C.c_int, [C.c_double, _dp, C.c_double, _dp, C.c_double, C.c_double, _dp]),
     "kmc_b200_fraction_of_scan_completed": (C.c_double, [C.c_double, C.c_double]),
     "kmc_b200_pseudo_time_stamp": (C.c_double, [C.c_double, C.c_double, C.c_double, C.c_double]),
+    "kmc_b200_oxts_to_pose": (C.c_int, [C.c_double] * 7 + [_dp]),
     "kmc_b200_shard_range": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kmc_b200_deskew_frame_device": (C.c_int, [_vp, _vp, C.c_int64, C.POINTER(FrameParams), C.c_int, _vp]),
     "kmc_b200_deskew_batch_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int64, C.c_int, _vp]),
     "kmc_b200_pseudo_time_stamps_device": (C.c_int, [_vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
+    "kmc_b200_pseudo_time_stamps_xy_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_synth_scans_device": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, _vp]),
     "kmc_b200_synth_frame_params": (C.c_int, [C.c_int32, C.c_uint64, C.c_int64, C.c_double, _vp, _vp]),
     "kmc_b200_handle_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_vp)]),
     "kmc_b200_handle_destroy": (C.c_int, [_vp]),
+    "kmc_b200_default_handle": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "kmc_b200_handle_device": (C.c_int, [_vp]),
     "kmc_b200_handle_capacity": (C.c_int64, [_vp]),
     "kmc_b200_deskew_frame_host": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(FrameParams), C.c_int]),
     "kmc_b200_deskew_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int]),
     "kmc_b200_deskew_batch_multi_gpu": (C.c_int, [C.POINTER(_vp), C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, C.c_int]),
+    "kmc_b200_pseudo_time_stamps_xy_host": (C.c_int, [_vp, _dp, _dp, C.c_int64, C.c_double, C.c_double, _dp]),
     "kmc_b200_deskew_bin_file": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.POINTER(FrameParams), C.POINTER(C.c_int64)]),
 }
 
@@ -181,6 +185,12 @@ def relative_pose_between_times(t1, P1, t2, P2, anchor, query):
     out = np.empty(16)
     check(lib().kmc_b200_relative_pose_between_times(t1, _ptr(_colmajor(P1, 4)), t2, _ptr(_colmajor(P2, 4)), anchor,
                                                      query, _ptr(out)))
+    return out.reshape(4, 4).T.copy()
+
+
+def oxts_to_pose(lat, lon, alt, roll, pitch, yaw, scale: float = 1.0):
+    out = np.empty(16)
+    check(lib().kmc_b200_oxts_to_pose(lat, lon, alt, roll, pitch, yaw, scale, _ptr(out)))
     return out.reshape(4, 4).T.copy()
 
 
@@ -298,6 +308,13 @@ class Handle:
         offs = np.ascontiguousarray(offsets, dtype=np.int64)
         prm = np.ascontiguousarray(params, dtype=FRAME_PARAMS_DTYPE)
         check(lib().kmc_b200_deskew_batch_host(self._h, in_ptr, out_ptr, offs.ctypes.data, prm.ctypes.data, prm.size, mode))
+
+    def pseudo_time_stamps(self, x: np.ndarray, y: np.ndarray, start: float, end: float) -> np.ndarray:
+        xs = np.ascontiguousarray(x, dtype=np.float64)
+        ys = np.ascontiguousarray(y, dtype=np.float64)
+        out = np.empty_like(xs)
+        check(lib().kmc_b200_pseudo_time_stamps_xy_host(self._h, _ptr(xs), _ptr(ys), xs.size, start, end, _ptr(out)))
+        return out
 
     def deskew_bin_file(self, path_in: str, path_out: str, params: FrameParams) -> int:
         n = C.c_int64()

@@ -292,6 +292,12 @@ double kmc_b200_pseudo_time_stamp(double x, double y, double scan_start, double 
   return scan_start + kmc_b200::host::FractionOfScanCompleted(x, y) * (scan_end - scan_start);
 }
 
+int kmc_b200_oxts_to_pose(double lat, double lon, double alt, double roll, double pitch, double yaw, double scale, double T[16]) {
+  if (!T) return Fail(KMC_B200_ERR_NULL_POINTER, "oxts_to_pose: null output");
+  kmc_b200::host::OxtsToPose(lat, lon, alt, roll, pitch, yaw, scale, T);
+  return KMC_B200_OK;
+}
+
 int kmc_b200_shard_range(int64_t n_items, int32_t n_parts, int32_t index, int64_t* begin, int64_t* end) {
   if (!begin || !end) return Fail(KMC_B200_ERR_NULL_POINTER, "shard_range: null argument");
   if (n_items < 0 || n_parts <= 0 || index < 0 || index >= n_parts) return Fail(KMC_B200_ERR_BAD_SIZE, "shard_range: bad arguments");
@@ -345,6 +351,19 @@ int kmc_b200_pseudo_time_stamps_device(const float* in, double* stamps, int64_t 
   KMC_CUDA_TRY(cudaGetDevice(&device));
   if (int rc = SmCount(device, &sm)) return rc;
   KMC_CUDA_TRY(kmc_b200::dev::LaunchPseudoTimeStamps(in, stamps, n, start, end, sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
+int kmc_b200_pseudo_time_stamps_xy_device(const double* x, const double* y, double* stamps, int64_t n, double start, double end,
+                                          void* stream) {
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_xy_device: negative n_points");
+  if (n == 0) return KMC_B200_OK;
+  if (!x || !y || !stamps) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_xy_device: null argument");
+  if (!Aligned(x, 8) || !Aligned(y, 8) || !Aligned(stamps, 8)) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_xy_device: misaligned buffer");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchPseudoTimeStampsXy(x, y, stamps, n, start, end, sm, static_cast<cudaStream_t>(stream)));
   return KMC_B200_OK;
 }
 
@@ -415,6 +434,20 @@ int kmc_b200_handle_create(int device, int64_t capacity_points, kmc_b200_handle*
 
 int kmc_b200_handle_destroy(kmc_b200_handle* h) {
   FreeHandle(h);
+  return KMC_B200_OK;
+}
+
+int kmc_b200_default_handle(int device, kmc_b200_handle** out) {
+  if (!out) return Fail(KMC_B200_ERR_NULL_POINTER, "default_handle: null output");
+  *out = nullptr;
+  if (device < 0 || device >= kMaxDevices) return Fail(KMC_B200_ERR_NO_DEVICE, "default_handle: device ordinal out of range");
+  static std::mutex mu;
+  static kmc_b200_handle* table[kMaxDevices] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (!table[device]) {
+    if (int rc = kmc_b200_handle_create(device, 250000, &table[device])) return rc;  // data_io.hpp:17 in the reference
+  }
+  *out = table[device];
   return KMC_B200_OK;
 }
 
@@ -498,6 +531,28 @@ int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_h
   for (auto& w : workers) w.join();
   for (int32_t i = 0; i < n_handles; ++i)
     if (status[i] != KMC_B200_OK) return Fail(status[i], "device " + std::to_string(handles[i]->device) + ": " + message[i]);
+  return KMC_B200_OK;
+}
+
+int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n, double start, double end,
+                                        double* stamps) {
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_xy_host: null handle");
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_xy_host: negative n_points");
+  if (n == 0) return KMC_B200_OK;
+  if (!x || !y || !stamps) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_xy_host: null argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  KMC_CUDA_TRY(cudaSetDevice(h->device));
+  double* d = nullptr;  // x | y | stamps
+  size_t const bytes = static_cast<size_t>(n) * sizeof(double);
+  KMC_CUDA_TRY(cudaMalloc(&d, 3 * bytes));
+  cudaStream_t const st = h->stream[0];
+  cudaError_t e = cudaMemcpyAsync(d, x, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, y, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = kmc_b200::dev::LaunchPseudoTimeStampsXy(d, d + n, d + 2 * n, n, start, end, h->sm_count, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(stamps, d + 2 * n, bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return FailCuda(e, "pseudo_time_stamps_xy_host");
   return KMC_B200_OK;
 }
 

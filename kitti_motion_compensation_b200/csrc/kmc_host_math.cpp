@@ -260,6 +260,26 @@ void FrameParamsFromTwist(const double xi[6], double x_req, kmc_b200_frame_param
   out->wide = (out->theta2 > KMC_B200_SERIES_THETA2_MAX) ? 1.0f : 0.0f;
 }
 
+void OxtsToPose(double lat, double lon, double alt, double roll, double pitch, double yaw, double scale, double T[16]) {
+  constexpr double kEarthRadius = 6378137.0;  // metres
+  double const cr = std::cos(roll), sr = std::sin(roll), cp = std::cos(pitch), sp = std::sin(pitch), cy = std::cos(yaw),
+               sy = std::sin(yaw);
+  // R = Rz(yaw) Ry(pitch) Rx(roll), written out
+  double R[9];
+  At3(R, 0, 0) = cy * cp;
+  At3(R, 0, 1) = cy * sp * sr - sy * cr;
+  At3(R, 0, 2) = cy * sp * cr + sy * sr;
+  At3(R, 1, 0) = sy * cp;
+  At3(R, 1, 1) = sy * sp * sr + cy * cr;
+  At3(R, 1, 2) = sy * sp * cr - cy * sr;
+  At3(R, 2, 0) = -sp;
+  At3(R, 2, 1) = cp * sr;
+  At3(R, 2, 2) = cp * cr;
+  double const t[3] = {scale * kEarthRadius * M_PI * lon / 180.0,
+                       scale * kEarthRadius * std::log(std::tan(M_PI * (90.0 + lat) / 360.0)), alt};
+  Join(R, t, T);
+}
+
 double FractionOfScanCompleted(double x, double y) { return (M_PI - std::atan2(y, x)) / (2.0 * M_PI); }
 
 }  // namespace kmc_b200::host

@@ -36,6 +36,9 @@ int PoseAtTime(double t1, const double P1[16], double t2, const double P2[16], d
 // Per-frame kernel constants from the scan twist and the requested fraction.
 void FrameParamsFromTwist(const double xi[6], double x_req, kmc_b200_frame_params* out);
 
-double FractionOfScanCompleted(double x, double y);                // timestamp_mocking.cpp:46
+double FractionOfScanCompleted(double x, double y);
+
+// OxtsToPose (data_io.cpp:68-88): Mercator projection for the position, Rz(yaw) Ry(pitch) Rx(roll) for the attitude.
+void OxtsToPose(double lat, double lon, double alt, double roll, double pitch, double yaw, double scale, double T[16]);                // timestamp_mocking.cpp:46
 
 }  // namespace kmc_b200::host

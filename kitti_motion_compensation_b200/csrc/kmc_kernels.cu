@@ -328,6 +328,16 @@ __global__ void __launch_bounds__(kBlockThreads)
   }
 }
 
+__global__ void __launch_bounds__(kBlockThreads)
+    PseudoTimeStampsXyKernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ stamps, int64_t n,
+                             double start, double duration) {
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; i < n; i += stride) {
+    double const frac = (3.14159265358979323846 - atan2(__ldg(y + i), __ldg(x + i))) / (2.0 * 3.14159265358979323846);
+    stamps[i] = start + frac * duration;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // seeded synthetic spinning-LiDAR scans, generated in HBM
 // ---------------------------------------------------------------------------------------------------------------
@@ -534,6 +544,17 @@ cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, d
   if (grid > cap) grid = cap;
   PseudoTimeStampsKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(reinterpret_cast<const float4*>(in), stamps, n,
                                                                                     start, end - start);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* stamps, int64_t n, double start, double end,
+                                     int sm_count, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
+  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  if (grid > cap) grid = cap;
+  PseudoTimeStampsXyKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(x, y, stamps, n, start, end - start);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

@@ -36,6 +36,9 @@ cudaError_t LaunchDeskewBatch(const float* in, float* out, const int64_t* offset
 cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,
                                    cudaStream_t stream);
 
+cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* stamps, int64_t n, double start, double end,
+                                     int sm_count, cudaStream_t stream);
+
 cudaError_t LaunchSynthScans(float* out, int64_t points_per_scan, int32_t n_scans, int32_t n_rings, uint64_t seed,
                              int64_t first_scan_index, int sm_count, cudaStream_t stream);
 

@@ -485,24 +485,26 @@ void ApplyTuneEnv(LaunchConfig& cfg) {
 uint64_t LaunchCount() { return g_launches.load(std::memory_order_relaxed); }
 
 LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_count) {
-  // Defaults from the B200 sweeps (profiles/sweep_r01*.json): one 256-bit load + one 256-bit store per thread per tile,
-  // plain ld/st, 4 CTAs x 256 threads per SM (32 KB of loads in flight per SM).  More bytes in flight per thread or more
-  // resident CTAs measured SLOWER (5.9 vs 6.5 TB/s): the kernel is at the copy ceiling and extra requests only lengthen
-  // the DRAM queues.
+  // Defaults from the B200 sweeps (profiles/r01_sweep_*.log): one 256-bit load + one 256-bit store per thread per tile,
+  // plain ld/st, 5 CTAs x 256 threads per SM (40 KB of loads in flight per SM), work items of 8 tiles.  The optimum is
+  // sharp: 3 / 4 / 5 / 6 CTAs per SM measured 5.8 / 6.35 / 6.5 / 6.05 TB/s, and more bytes in flight per thread
+  // (2-4 loads) measured 5.9-6.1 TB/s — at the copy ceiling extra requests only lengthen the DRAM queues.
   LaunchConfig cfg;
   cfg.vec = 2;
   cfg.unroll = 1;
   cfg.hint = 0;
   cfg.block = 256;
-  cfg.ctas_per_sm = 4;
-  cfg.item_tiles = 16;
-  // Small inputs are latency bound: spread them over as many CTAs as possible.
+  cfg.ctas_per_sm = 5;
+  cfg.item_tiles = 8;
+  // Mid-size inputs: keep >= 16 work items per resident CTA so the tail stays small; tiny inputs (latency bound):
+  // one tile per item and 128-bit accesses to spread over as many CTAs as possible.
   int64_t const tile = static_cast<int64_t>(cfg.block) * cfg.unroll * cfg.vec;
   int64_t const resident = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm;
-  if (n_points < resident * tile * cfg.item_tiles * 4) {
-    int64_t const per_cta_tiles = n_points / (resident * tile);
-    cfg.item_tiles = per_cta_tiles >= 8 ? 4 : 1;
-    if (n_points < resident * tile) cfg.vec = 1;
+  int64_t const tiles_per_cta = n_points / (resident * tile);
+  if (tiles_per_cta < 16 * cfg.item_tiles) {
+    int64_t const t = tiles_per_cta / 16;
+    cfg.item_tiles = static_cast<int>(t < 1 ? 1 : t);
+    if (tiles_per_cta < 1) cfg.vec = 1;
   }
   ApplyTuneEnv(cfg);
   if (!aligned32) cfg.vec = 1;

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Measures the BASELINE.json configs that are not bench.py's headline line (run under gpurun, one GPU):
+
+  config 1  real KITTI scan (drive_0005 frame 0, 123 397 points) — single-frame kernel latency + parity vs the oracle
+  config 2  one synthetic 130 000-point scan — single-frame kernel latency (L2-resident: a latency, not a bandwidth, number)
+  config 5  one dense 10 M-point 128-beam frame — single-frame kernel bandwidth (320 MB of traffic > L2)
+  + the C ABI host call (H2D + kernel + D2H) for one scan from pageable and from pinned memory.
+
+Writes gpurun_out/configs.json.  The oracle is used here only as the checker / CPU timing of config 1.
+"""
+import json
+import os
+import statistics
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from kitti_motion_compensation_b200 import capi  # noqa: E402
+
+
+def time_launches(fn, reps=200, flush=None):
+    for _ in range(5):
+        fn()
+    ms = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()  # evict the working set from L2 between launches
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return statistics.median(ms), min(ms)
+
+
+def main():
+    import helpers
+    from oracle import binding as ob
+    torch.cuda.set_device(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # 256 MB > 126 MB L2
+
+    # ---- config 1 ---------------------------------------------------------------------------------------------------
+    pts = helpers.real_scan()
+    T_start, T_end, t0, t1, t2 = helpers.config1_frame()
+    p = capi.frame_params_from_poses(T_start, T_end, t0, t2, t1)
+    d_in = torch.from_numpy(pts).cuda()
+    d_out = torch.empty_like(d_in)
+    fn = lambda: capi.deskew_frame_device(d_in.data_ptr(), d_out.data_ptr(), len(pts), p, 0, stream)  # noqa: E731
+    warm_med, warm_min = time_launches(fn)
+    cold_med, cold_min = time_launches(fn, reps=50, flush=flush)
+    tc = time.perf_counter()
+    ref = ob.deskew_xyzi_scan(pts, T_start, T_end, t0, t2, t1)
+    cpu_s = time.perf_counter() - tc
+    err = float(np.abs(d_out.cpu().numpy()[:, :3].astype(np.float64) - ref[:, :3]).max())
+    out["config1_real_scan"] = {"points": len(pts), "kernel_us_l2_warm_median": warm_med * 1e3, "kernel_us_l2_warm_best": warm_min * 1e3,
+                                "kernel_us_l2_flushed_median": cold_med * 1e3, "mpoints_per_s_flushed": len(pts) / (cold_med * 1e-3) / 1e6,
+                                "oracle_cpu_seconds_1_thread": cpu_s, "oracle_mpoints_per_s_1_thread": len(pts) / cpu_s / 1e6,
+                                "max_abs_err_m": err}
+
+    # ---- config 2 ---------------------------------------------------------------------------------------------------
+    n = 130_000
+    d_in = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(d_in.data_ptr(), n, 1, 64, 20110926, 0, stream)
+    d_out = torch.empty_like(d_in)
+    params, xi = capi.synth_frame_params(1, 20110926, 0, 0.5)
+    p = capi.FrameParams.from_buffer_copy(params.tobytes())
+    fn = lambda: capi.deskew_frame_device(d_in.data_ptr(), d_out.data_ptr(), n, p, 0, stream)  # noqa: E731
+    warm_med, warm_min = time_launches(fn)
+    cold_med, _ = time_launches(fn, reps=50, flush=flush)
+    host_pts = d_in.cpu().numpy()
+    ref = ob.deskew_xyzi_scan(host_pts[::4], np.eye(4), ob.se3_exp(xi[0]), 0.0, 0.1, 0.05)
+    err = float(np.abs(d_out.cpu().numpy()[::4, :3].astype(np.float64) - ref[:, :3]).max())
+    out["config2_synthetic_130k"] = {"points": n, "kernel_us_l2_warm_median": warm_med * 1e3, "kernel_us_l2_warm_best": warm_min * 1e3,
+                                     "kernel_us_l2_flushed_median": cold_med * 1e3, "mpoints_per_s_l2_warm": n / (warm_med * 1e-3) / 1e6,
+                                     "max_abs_err_m": err}
+    # host entry point for one scan: pageable and pinned
+    with capi.Handle(0, 250_000) as h:
+        res = np.empty_like(host_pts)
+        for _ in range(3):
+            h.deskew_frame(host_pts, p, out=res)
+        t = []
+        for _ in range(30):
+            a = time.perf_counter()
+            h.deskew_frame(host_pts, p, out=res)
+            t.append(time.perf_counter() - a)
+        pin_in = torch.from_numpy(host_pts).pin_memory()
+        pin_out = torch.empty_like(pin_in).pin_memory()
+        for _ in range(3):
+            h.deskew_frame_ptr(pin_in.data_ptr(), pin_out.data_ptr(), n, p)
+        tp = []
+        for _ in range(30):
+            a = time.perf_counter()
+            h.deskew_frame_ptr(pin_in.data_ptr(), pin_out.data_ptr(), n, p)
+            tp.append(time.perf_counter() - a)
+        out["config2_host_call"] = {"pageable_us_median": statistics.median(t) * 1e6, "pinned_us_median": statistics.median(tp) * 1e6,
+                                    "pinned_mpoints_per_s": n / statistics.median(tp) / 1e6}
+
+    # ---- config 5 ---------------------------------------------------------------------------------------------------
+    n = 10_000_000
+    d_in = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(d_in.data_ptr(), n, 1, 128, 20110926, 0, stream)
+    d_out = torch.empty_like(d_in)
+    fn = lambda: capi.deskew_frame_device(d_in.data_ptr(), d_out.data_ptr(), n, p, 0, stream)  # noqa: E731
+    med, best = time_launches(fn, reps=50, flush=flush)
+    out["config5_dense_10m"] = {"points": n, "kernel_us_median": med * 1e3, "kernel_us_best": best * 1e3,
+                                "mpoints_per_s": n / (med * 1e-3) / 1e6, "gb_per_s_32B_per_point": 32 * n / (med * 1e-3) / 1e9}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/sweep.json")
+    ap.add_argument("--tunes", default=None, help="semicolon-separated KMC_B200_TUNE strings to time instead of the staged sweep")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     n = args.scans * args.points
@@ -65,12 +66,18 @@ def main():
         results.append({"shape": tune, "median_gbs": gbs(med), "best_gbs": gbs(best)})
         return gbs(med)
 
+    if args.tunes:
+        for tune in args.tunes.split(";"):
+            run(tune.strip())
+        args.staged = False
+    else:
+        args.staged = True
     stage1 = {}
-    for v, u, h, blk in itertools.product((1, 2), (1, 2), (0, 1), (128, 256, 512)):
+    for v, u, h, blk in (itertools.product((1, 2), (1, 2), (0, 1), (128, 256, 512)) if args.staged else ()):
         ctas = 1024 // blk  # same resident threads per SM
         stage1[(v, u, h, blk)] = run(f"vec={v},unroll={u},hint={h},block={blk},ctas={ctas},item_tiles=16")
-    v, u, h, blk = max(stage1, key=stage1.get)
-    for threads, tiles in itertools.product((768, 1024, 1280, 1536), (4, 8, 16, 32)):
+    v, u, h, blk = max(stage1, key=stage1.get) if stage1 else (2, 1, 0, 256)
+    for threads, tiles in (itertools.product((768, 1024, 1280, 1536), (4, 8, 16, 32)) if args.staged else ()):
         if threads % blk:
             continue
         run(f"vec={v},unroll={u},hint={h},block={blk},ctas={threads // blk},item_tiles={tiles}")

@@ -485,3 +485,38 @@ def test_config5_dense_10m_point_frame(capi, oracle, cuda):
     # the last points of the frame (tail tiles) are written
     tail_in, tail_out = d_in[-3000:].cpu().numpy(), d_out[-3000:].cpu().numpy()
     assert np.abs(tail_out[:, :3] - helpers.closed_form_deskew(tail_in, xi, 0.5)).max() < TOL_M
+
+
+def test_device_entry_points_capture_into_a_cuda_graph(capi, cuda):
+    """Launch-bound streams of single frames (a 130 K-point scan is ~8 us of kernel) can be captured once and replayed:
+    the device entry points make no synchronising call, so they are legal inside stream capture."""
+    torch = cuda
+    n, frames = 20_000, 8
+    params, xi = capi.synth_frame_params(frames, 7, 0, 0.5)
+    recs = [capi.FrameParams.from_buffer_copy(params[f:f + 1].tobytes()) for f in range(frames)]
+    d_in = torch.empty((frames * n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(d_in.data_ptr(), n, frames, 64, 7, 0)
+    eager = torch.empty_like(d_in)
+    for f in range(frames):
+        capi.deskew_frame_device(d_in[f * n:].data_ptr(), eager[f * n:].data_ptr(), n, recs[f], 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    replayed = torch.zeros_like(d_in)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.graph(graph, stream=side):
+        for f in range(frames):
+            capi.deskew_frame_device(d_in[f * n:].data_ptr(), replayed[f * n:].data_ptr(), n, recs[f], 0,
+                                     torch.cuda.current_stream().cuda_stream)
+        d_off = None
+    assert float(replayed.abs().max()) == 0.0  # nothing ran during capture
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(replayed, eager)
+    # new input contents, same graph
+    d_in.mul_(0.5)
+    graph.replay()
+    torch.cuda.synchronize()
+    for f in (0, frames - 1):
+        pts = d_in[f * n:(f + 1) * n].cpu().numpy()
+        cf = helpers.closed_form_deskew(pts, xi[f], 0.5)
+        assert np.abs(replayed[f * n:(f + 1) * n, :3].cpu().numpy() - cf).max() < TOL_M

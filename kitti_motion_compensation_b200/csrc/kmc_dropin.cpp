@@ -396,8 +396,27 @@ KMC_EXPORT void CopyOverUncompensatedFirstAndLastFrame(Path const run_folder) {
   }
 }
 
+namespace {
+
+std::vector<float> ReadBin(Path const& file) {
+  std::ifstream in{file, std::ios::in | std::ios::binary | std::ios::ate};
+  if (!in.is_open()) throw std::runtime_error("Unable to open requested KITTI pointcloud binary file: " + file.string());
+  std::int64_t const bytes{static_cast<std::int64_t>(in.tellg())};
+  if (bytes < 0 || bytes % 16 != 0) throw std::runtime_error("Opened KITTI pointcloud binary file is incorrectly formatted: " + file.string());
+  std::vector<float> data(static_cast<size_t>(bytes / 4));
+  in.seekg(0, std::ios::beg);
+  in.read(reinterpret_cast<char*>(data.data()), bytes);
+  return data;
+}
+
+}  // namespace
+
+// The reference handles one frame at a time (load three oxts packets, load + expand the scan, deskew, write).  Here a
+// run is processed in groups of up to kRunGroupFrames frames: the scans of a group are concatenated in their on-disk
+// float32 form and go through ONE pipelined batched pass (kmc_b200_deskew_batch_host), then every file is written.
 KMC_EXPORT void MotionCompensateRun(Path const run_folder) {
   namespace fs = std::filesystem;
+  constexpr size_t kRunGroupFrames = 256;  // ~0.5 GB of scans per direction
   Path const velodyne{run_folder / Path{"velodyne_points"}};
   size_t const n_frames{NumberOfFilesInDirectory(velodyne / Path("data"))};
   Path const out_folder{velodyne / Path("data_motion_compensated")};
@@ -405,27 +424,43 @@ KMC_EXPORT void MotionCompensateRun(Path const run_folder) {
   CopyOverUncompensatedFirstAndLastFrame(run_folder);
   if (n_frames < 3) return;
 
-  // all oxts packets and scan stamps once (the reference re-reads three packets per frame)
-  std::vector<Oxts> oxts;
+  std::vector<Oxts> oxts;  // every packet once (the reference re-reads three per frame)
   for (size_t i{0}; i < n_frames; ++i) oxts.push_back(LoadOxts(run_folder, i));
   kmc_b200_handle* handle{DefaultHandle()};
-  for (size_t i{1}; i + 1 < n_frames; ++i) {
-    Time const start{LoadTimeStamp(velodyne / Path("timestamps_start.txt"), i)};
-    Time const middle{LoadTimeStamp(velodyne / Path("timestamps.txt"), i)};
-    Time const end{LoadTimeStamp(velodyne / Path("timestamps_end.txt"), i)};
-    Affine3d const T_start{trajectory_interpolation::InterpolateTrajectory(oxts[i - 1], oxts[i], start)};
-    Affine3d const T_end{trajectory_interpolation::InterpolateTrajectory(oxts[i], oxts[i + 1], end)};
-    double p1[16], p2[16];
-    ToBuffer(T_start, p1);
-    ToBuffer(T_end, p2);
-    kmc_b200_frame_params params{};
-    int const rc = kmc_b200_frame_params_from_poses(p1, p2, start, end, middle, &params);
-    if (rc == KMC_B200_ERR_TIME_OUT_OF_RANGE || rc == KMC_B200_ERR_EMPTY_INTERVAL) AbortOutOfRange("MotionCompensateRun", middle, start, end);
-    ThrowUnlessOk(rc, "kmc_b200_frame_params_from_poses");
-    std::string const stem{IdToZeroPaddedString(i) + ".bin"};
-    ThrowUnlessOk(kmc_b200_deskew_bin_file(handle, (velodyne / Path("data") / stem).c_str(), (out_folder / stem).c_str(), &params, nullptr),
-                  "kmc_b200_deskew_bin_file");
-    std::cout << "Motion compensated pointcloud number: " << i << std::endl;
+
+  for (size_t group_begin{1}; group_begin + 1 < n_frames; group_begin += kRunGroupFrames) {
+    size_t const group_end{std::min(group_begin + kRunGroupFrames, n_frames - 1)};
+    std::vector<float> scans;
+    std::vector<std::int64_t> offsets{0};
+    std::vector<kmc_b200_frame_params> params;
+    for (size_t i{group_begin}; i < group_end; ++i) {
+      Time const start{LoadTimeStamp(velodyne / Path("timestamps_start.txt"), i)};
+      Time const middle{LoadTimeStamp(velodyne / Path("timestamps.txt"), i)};  // camera trigger = requested time
+      Time const end{LoadTimeStamp(velodyne / Path("timestamps_end.txt"), i)};
+      Affine3d const T_start{trajectory_interpolation::InterpolateTrajectory(oxts[i - 1], oxts[i], start)};
+      Affine3d const T_end{trajectory_interpolation::InterpolateTrajectory(oxts[i], oxts[i + 1], end)};
+      double p1[16], p2[16];
+      ToBuffer(T_start, p1);
+      ToBuffer(T_end, p2);
+      kmc_b200_frame_params rec{};
+      int const rc = kmc_b200_frame_params_from_poses(p1, p2, start, end, middle, &rec);
+      if (rc == KMC_B200_ERR_TIME_OUT_OF_RANGE || rc == KMC_B200_ERR_EMPTY_INTERVAL) AbortOutOfRange("MotionCompensateRun", middle, start, end);
+      ThrowUnlessOk(rc, "kmc_b200_frame_params_from_poses");
+      params.push_back(rec);
+      std::vector<float> const scan{ReadBin(velodyne / Path("data") / (IdToZeroPaddedString(i) + ".bin"))};
+      scans.insert(scans.end(), scan.begin(), scan.end());
+      offsets.push_back(static_cast<std::int64_t>(scans.size() / 4));
+    }
+    std::vector<float> result(scans.size());
+    ThrowUnlessOk(kmc_b200_deskew_batch_host(handle, scans.data(), result.data(), offsets.data(), params.data(),
+                                             static_cast<std::int32_t>(params.size()), KMC_B200_TIME_FROM_AZIMUTH),
+                  "kmc_b200_deskew_batch_host");
+    for (size_t i{group_begin}; i < group_end; ++i) {
+      size_t const k{i - group_begin};
+      std::ofstream out(out_folder / (IdToZeroPaddedString(i) + ".bin"), std::ios::out | std::ios::binary);
+      out.write(reinterpret_cast<const char*>(result.data() + 4 * offsets[k]), static_cast<std::streamsize>(16 * (offsets[k + 1] - offsets[k])));
+      std::cout << "Motion compensated pointcloud number: " << i << std::endl;
+    }
   }
 }
 

@@ -14,6 +14,17 @@
 #include "kitti_motion_compensation/motion_compensation.hpp"
 #include "kitti_motion_compensation/timestamp_mocking.hpp"
 
+#include <stdexcept>
+
+#include "kitti_motion_compensation/data_io.hpp"
+
+// trajectory_interpolation.cpp:21-25 (the Oxts constructor) references kmc::OxtsToPose, which lives in data_io.cpp
+// together with the OpenCV image loaders and is therefore not compiled into oracle/_ref.  The deskew path never takes
+// that constructor; this definition only satisfies the dynamic linker.
+namespace kmc {
+Eigen::Affine3d OxtsToPose(Oxts const&, double const) { throw std::logic_error("OxtsToPose is not part of oracle/_ref"); }
+}  // namespace kmc
+
 namespace {
 
 kmc::Affine3d FromColMajor(const double* m) {

@@ -88,6 +88,20 @@ typedef struct kmc_b200_frame_params {
 /* Largest theta^2 (rad^2 per scan) handled by the short in-kernel power series. */
 #define KMC_B200_SERIES_THETA2_MAX 1.0f
 
+/* Per-camera constants of the projection kernels (reference camera_model.cpp:5-36,38-95):
+ *   rect = R_rect_00 * (R|T)_velo_to_cam            3x4 row-major, X_rect = rect * (x y z 1)
+ *   pix  = P_rect_xx * [rect; 0 0 0 1]              3x4 row-major, (u v) = (pix*X)[0,1] / (pix*X)[2]
+ * A point is culled when z_rect < min_depth (0.01), z_rect > max_range (15) or y_rect > max_below (1.25);
+ * color_gain = 255 / (max_range - 0.01) is the reference's range colouring. */
+typedef struct kmc_b200_camera_params {
+  float rect[12];
+  float pix[12];
+  float min_depth;
+  float max_range;
+  float max_below;
+  float color_gain;
+} kmc_b200_camera_params;
+
 typedef struct kmc_b200_handle kmc_b200_handle; /* opaque: device + stream + pinned/device staging (the "DataHandle") */
 
 /* ---- library ------------------------------------------------------------------------------------------------ */
@@ -130,6 +144,12 @@ KMC_B200_API double kmc_b200_pseudo_time_stamp(double x, double y, double scan_s
 KMC_B200_API int kmc_b200_oxts_to_pose(double lat, double lon, double alt, double roll, double pitch, double yaw, double scale,
                                        double T_colmajor[16]);
 
+/* Camera constants from the KITTI calibration: P_rect_xx (3x4), R_rect_00 (3x3) and the velodyne -> camera_00 transform
+ * (4x4), all column-major doubles (Eigen's .data()); max_range as in ProjectPointcloudOnImage (default 15 m). */
+KMC_B200_API int kmc_b200_camera_params_from_calibration(const double P_rect_colmajor[12], const double R_rect_00_colmajor[9],
+                                                         const double T_velo_to_cam_colmajor[16], double max_range,
+                                                         kmc_b200_camera_params* out);
+
 /* Contiguous split of n_items over n_parts (frame sharding across GPUs): part `index` owns [*begin, *end). */
 KMC_B200_API int kmc_b200_shard_range(int64_t n_items, int32_t n_parts, int32_t index, int64_t* begin, int64_t* end);
 
@@ -152,6 +172,18 @@ KMC_B200_API int kmc_b200_pseudo_time_stamps_device(const float* xyzi_in, double
  * matrix (Pointcloud::data() and data() + N), device pointers. */
 KMC_B200_API int kmc_b200_pseudo_time_stamps_xy_device(const double* x, const double* y, double* stamps_out, int64_t n_points,
                                                        double scan_start, double scan_end, void* stream);
+/* Projection of a scan onto one rectified camera — the per-point part of viz::ProjectPointcloudOnFrame/-OnImage
+ * (camera_model.cpp:5-36,38-95); the cv::circle drawing stays with the caller.  For every point the kernel writes
+ * one float4 (u, v, z_rect, c): pixel coordinates before the reference's int truncation, depth in front of the camera,
+ * and c = the reference's colour scale 255 z/(max_range - 0.01) for kept points or -1 for culled ones. */
+KMC_B200_API int kmc_b200_project_frame_device(const float* xyzi_in, float* uvzc_out, int64_t n_points,
+                                               const kmc_b200_camera_params* camera_host, void* stream);
+/* Deskew and projection of the DESKEWED point in one pass (48 B/point instead of 32 + 32): what
+ * GenerateProjectionVisualizationOfRun does in two steps (handlers.cpp:83-87).  xyzi_out may be NULL to skip writing
+ * the deskewed cloud (32 B/point). */
+KMC_B200_API int kmc_b200_deskew_project_frame_device(const float* xyzi_in, float* xyzi_out, float* uvzc_out, int64_t n_points,
+                                                      const kmc_b200_frame_params* params_host,
+                                                      const kmc_b200_camera_params* camera_host, int time_mode, void* stream);
 /* Seeded synthetic HDL-64E style scans written straight into device memory (benchmark input):
  * n_scans scans of points_per_scan points, scan k uses seed + first_scan_index + k, so a scan's content does not
  * depend on which GPU generates it.  n_rings x azimuth steps, ring-major, log-uniform range in [2, 120) m. */

@@ -40,6 +40,12 @@ class FrameParams(C.Structure):
     ]
 
 
+class CameraParams(C.Structure):
+    """kmc_b200_camera_params (112 bytes)."""
+    _fields_ = [("rect", C.c_float * 12), ("pix", C.c_float * 12), ("min_depth", C.c_float), ("max_range", C.c_float),
+                ("max_below", C.c_float), ("color_gain", C.c_float)]
+
+
 FRAME_PARAMS_DTYPE = np.dtype([
     ("phi", np.float32, 3), ("theta2", np.float32), ("rho_perp", np.float32, 3), ("c0", np.float32),
     ("rho_par", np.float32, 3), ("x_req", np.float32), ("phi_x_rho", np.float32, 3), ("wide", np.float32)])
@@ -77,9 +83,13 @@ SIGNATURES = {
     "kmc_b200_fraction_of_scan_completed": (C.c_double, [C.c_double, C.c_double]),
     "kmc_b200_pseudo_time_stamp": (C.c_double, [C.c_double, C.c_double, C.c_double, C.c_double]),
     "kmc_b200_oxts_to_pose": (C.c_int, [C.c_double] * 7 + [_dp]),
+    "kmc_b200_camera_params_from_calibration": (C.c_int, [_dp, _dp, _dp, C.c_double, C.POINTER(CameraParams)]),
     "kmc_b200_shard_range": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kmc_b200_deskew_frame_device": (C.c_int, [_vp, _vp, C.c_int64, C.POINTER(FrameParams), C.c_int, _vp]),
     "kmc_b200_deskew_batch_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int64, C.c_int, _vp]),
+    "kmc_b200_project_frame_device": (C.c_int, [_vp, _vp, C.c_int64, C.POINTER(CameraParams), _vp]),
+    "kmc_b200_deskew_project_frame_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(FrameParams), C.POINTER(CameraParams),
+                                                       C.c_int, _vp]),
     "kmc_b200_pseudo_time_stamps_device": (C.c_int, [_vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_pseudo_time_stamps_xy_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_synth_scans_device": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, _vp]),
@@ -194,6 +204,14 @@ def oxts_to_pose(lat, lon, alt, roll, pitch, yaw, scale: float = 1.0):
     return out.reshape(4, 4).T.copy()
 
 
+def camera_params_from_calibration(P_rect_3x4, R_rect_00, T_velo_to_cam, max_range: float = 15.0) -> CameraParams:
+    out = CameraParams()
+    P = np.ascontiguousarray(np.asarray(P_rect_3x4, dtype=np.float64).T).reshape(-1)  # 3x4 -> column-major
+    check(lib().kmc_b200_camera_params_from_calibration(_ptr(P), _ptr(_colmajor(R_rect_00, 3)), _ptr(_colmajor(T_velo_to_cam, 4)),
+                                                        max_range, C.byref(out)))
+    return out
+
+
 def fraction_of_scan_completed(x: float, y: float) -> float:
     return lib().kmc_b200_fraction_of_scan_completed(x, y)
 
@@ -226,6 +244,16 @@ def deskew_batch_device(in_ptr: int, out_ptr: int, offsets_ptr: int, params_ptr:
                         mode: int = TIME_FROM_AZIMUTH, stream: int = 0) -> None:
     check(lib().kmc_b200_deskew_batch_device(in_ptr, out_ptr, offsets_ptr, params_ptr, n_frames, n_points_total, mode,
                                              stream))
+
+
+def project_frame_device(in_ptr: int, uvzc_ptr: int, n_points: int, camera: CameraParams, stream: int = 0) -> None:
+    check(lib().kmc_b200_project_frame_device(in_ptr, uvzc_ptr, n_points, C.byref(camera), stream))
+
+
+def deskew_project_frame_device(in_ptr: int, out_ptr: int, uvzc_ptr: int, n_points: int, params: FrameParams, camera: CameraParams,
+                                mode: int = TIME_FROM_AZIMUTH, stream: int = 0) -> None:
+    check(lib().kmc_b200_deskew_project_frame_device(in_ptr, out_ptr, uvzc_ptr, n_points, C.byref(params), C.byref(camera), mode,
+                                                     stream))
 
 
 def pseudo_time_stamps_device(in_ptr: int, out_ptr: int, n_points: int, start: float, end: float, stream: int = 0) -> None:

@@ -298,6 +298,14 @@ int kmc_b200_oxts_to_pose(double lat, double lon, double alt, double roll, doubl
   return KMC_B200_OK;
 }
 
+int kmc_b200_camera_params_from_calibration(const double P_rect[12], const double R_rect_00[9], const double T_velo_to_cam[16],
+                                            double max_range, kmc_b200_camera_params* out) {
+  if (!P_rect || !R_rect_00 || !T_velo_to_cam || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "camera_params_from_calibration: null argument");
+  if (!(max_range > 0.01)) return Fail(KMC_B200_ERR_BAD_SIZE, "camera_params_from_calibration: max_range must exceed 0.01 m");
+  kmc_b200::host::CameraParamsFromCalibration(P_rect, R_rect_00, T_velo_to_cam, max_range, out);
+  return KMC_B200_OK;
+}
+
 int kmc_b200_shard_range(int64_t n_items, int32_t n_parts, int32_t index, int64_t* begin, int64_t* end) {
   if (!begin || !end) return Fail(KMC_B200_ERR_NULL_POINTER, "shard_range: null argument");
   if (n_items < 0 || n_parts <= 0 || index < 0 || index >= n_parts) return Fail(KMC_B200_ERR_BAD_SIZE, "shard_range: bad arguments");
@@ -340,6 +348,36 @@ int kmc_b200_deskew_batch_device(const float* in, float* out, const int64_t* off
   KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(in, out, offsets_dev, params_dev, n_frames, n_total, 0, n_total, mode, cfg, sm,
                                                 static_cast<cudaStream_t>(stream)));
   return KMC_B200_OK;
+}
+
+namespace {
+int ProjectCommon(const char* who, const float* in, float* cloud_out, float* pix_out, int64_t n, const kmc_b200_frame_params* params,
+                  const kmc_b200_camera_params* camera, int mode, void* stream) {
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, std::string(who) + ": negative n_points");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, std::string(who) + ": unknown time mode");
+  if (!camera) return Fail(KMC_B200_ERR_NULL_POINTER, std::string(who) + ": null camera params");
+  if (n == 0) return KMC_B200_OK;
+  if (!in || !pix_out) return Fail(KMC_B200_ERR_NULL_POINTER, std::string(who) + ": null point buffer");
+  if (!Aligned(in, 16) || !Aligned(pix_out, 16) || (cloud_out && !Aligned(cloud_out, 16)))
+    return Fail(KMC_B200_ERR_BAD_SIZE, std::string(who) + ": buffers must be 16-byte aligned");
+  if (pix_out == in || pix_out == cloud_out) return Fail(KMC_B200_ERR_BAD_SIZE, std::string(who) + ": the pixel buffer must not alias the clouds");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  bool const vec2 = Aligned(in, 32) && Aligned(pix_out, 32) && (!cloud_out || Aligned(cloud_out, 32));
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchProject(in, cloud_out, pix_out, n, params, *camera, mode, vec2, sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+}  // namespace
+
+int kmc_b200_project_frame_device(const float* in, float* uvzc_out, int64_t n, const kmc_b200_camera_params* camera, void* stream) {
+  return ProjectCommon("project_frame_device", in, nullptr, uvzc_out, n, nullptr, camera, KMC_B200_TIME_FROM_AZIMUTH, stream);
+}
+
+int kmc_b200_deskew_project_frame_device(const float* in, float* xyzi_out, float* uvzc_out, int64_t n, const kmc_b200_frame_params* params,
+                                         const kmc_b200_camera_params* camera, int mode, void* stream) {
+  if (!params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_project_frame_device: null frame params");
+  return ProjectCommon("deskew_project_frame_device", in, xyzi_out, uvzc_out, n, params, camera, mode, stream);
 }
 
 int kmc_b200_pseudo_time_stamps_device(const float* in, double* stamps, int64_t n, double start, double end, void* stream) {

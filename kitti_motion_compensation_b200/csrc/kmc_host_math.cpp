@@ -280,6 +280,33 @@ void OxtsToPose(double lat, double lon, double alt, double roll, double pitch, d
   Join(R, t, T);
 }
 
+void CameraParamsFromCalibration(const double P_rect[12], const double R_rect_00[9], const double T_velo_to_cam[16],
+                                 double max_range, kmc_b200_camera_params* out) {
+  double L[9], t[3], rect[3][4], pix[3][4];
+  Split(T_velo_to_cam, L, t);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c)
+      rect[r][c] = At3(R_rect_00, r, 0) * At3(L, 0, c) + At3(R_rect_00, r, 1) * At3(L, 1, c) + At3(R_rect_00, r, 2) * At3(L, 2, c);
+    rect[r][3] = At3(R_rect_00, r, 0) * t[0] + At3(R_rect_00, r, 1) * t[1] + At3(R_rect_00, r, 2) * t[2];
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) {
+      // P_rect is 3x4 column-major: P(r, k) = P_rect[k * 3 + r]; the homogeneous row of [rect; 0 0 0 1] only feeds column 3
+      double acc = P_rect[0 * 3 + r] * rect[0][c] + P_rect[1 * 3 + r] * rect[1][c] + P_rect[2 * 3 + r] * rect[2][c];
+      if (c == 3) acc += P_rect[3 * 3 + r];
+      pix[r][c] = acc;
+    }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) {
+      out->rect[r * 4 + c] = static_cast<float>(rect[r][c]);
+      out->pix[r * 4 + c] = static_cast<float>(pix[r][c]);
+    }
+  out->min_depth = 0.01f;
+  out->max_range = static_cast<float>(max_range);
+  out->max_below = 1.25f;
+  out->color_gain = static_cast<float>(255.0 / (max_range - 0.01));
+}
+
 double FractionOfScanCompleted(double x, double y) { return (M_PI - std::atan2(y, x)) / (2.0 * M_PI); }
 
 }  // namespace kmc_b200::host

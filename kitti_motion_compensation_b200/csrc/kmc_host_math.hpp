@@ -41,4 +41,9 @@ double FractionOfScanCompleted(double x, double y);
 // OxtsToPose (data_io.cpp:68-88): Mercator projection for the position, Rz(yaw) Ry(pitch) Rx(roll) for the attitude.
 void OxtsToPose(double lat, double lon, double alt, double roll, double pitch, double yaw, double scale, double T[16]);                // timestamp_mocking.cpp:46
 
+// rect = R_rect_00 * T_velo_to_cam (3x4), pix = P_rect * [rect; 0 0 0 1] (3x4), composed in double
+// (camera_model.cpp:9,75,78-81); inputs column-major.
+void CameraParamsFromCalibration(const double P_rect[12], const double R_rect_00[9], const double T_velo_to_cam[16],
+                                 double max_range, kmc_b200_camera_params* out);
+
 }  // namespace kmc_b200::host

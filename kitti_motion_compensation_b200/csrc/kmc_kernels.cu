@@ -315,6 +315,64 @@ __global__ void __launch_bounds__(BLOCK)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Projection onto a rectified camera (camera_model.cpp:5-36,38-95 without the drawing), optionally fused behind the
+// deskew: one pass reads a point, (deskews it,) writes the (deskewed) point and its pixel record.
+// Streaming map, HBM bound: 32 B/point (project only, or deskew+project without the cloud output), 48 B/point (both).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ProjectPoint(float4 p, const kmc_b200_camera_params& K) {
+  float const xr = fmaf(K.rect[0], p.x, fmaf(K.rect[1], p.y, fmaf(K.rect[2], p.z, K.rect[3])));
+  float const yr = fmaf(K.rect[4], p.x, fmaf(K.rect[5], p.y, fmaf(K.rect[6], p.z, K.rect[7])));
+  float const zr = fmaf(K.rect[8], p.x, fmaf(K.rect[9], p.y, fmaf(K.rect[10], p.z, K.rect[11])));
+  float const pu = fmaf(K.pix[0], p.x, fmaf(K.pix[1], p.y, fmaf(K.pix[2], p.z, K.pix[3])));
+  float const pv = fmaf(K.pix[4], p.x, fmaf(K.pix[5], p.y, fmaf(K.pix[6], p.z, K.pix[7])));
+  float const pw = fmaf(K.pix[8], p.x, fmaf(K.pix[9], p.y, fmaf(K.pix[10], p.z, K.pix[11])));
+  float const inv = 1.0f / pw;  // IEEE division: pixel coordinates are compared at the 1e-2 px level
+  bool const culled = (zr < K.min_depth) || (zr > K.max_range) || (yr > K.max_below);
+  (void)xr;
+  return make_float4(pu * inv, pv * inv, zr, culled ? -1.0f : zr * K.color_gain);
+}
+
+template <bool DESKEW, bool WRITE_CLOUD, int MODE, bool VEC2>
+__global__ void __launch_bounds__(kBlockThreads)
+    ProjectFrameKernel(const float4* __restrict__ in, float4* __restrict__ cloud_out, float4* __restrict__ pix_out, int64_t n,
+                       const __grid_constant__ kmc_b200_frame_params P, const __grid_constant__ kmc_b200_camera_params K) {
+  if constexpr (!VEC2) {  // buffers only 16-byte aligned: one point per 128-bit access
+    int64_t const stride1 = static_cast<int64_t>(gridDim.x) * kBlockThreads;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; j < n; j += stride1) {
+      float4 p = LoadPoint<0>(in + j);
+      if constexpr (DESKEW) {
+        p = DeskewPoint<MODE>(p, P);
+        if constexpr (WRITE_CLOUD) StorePoint<0>(cloud_out + j, p);
+      }
+      StorePoint<0>(pix_out + j, ProjectPoint(p, K));
+    }
+    return;
+  }
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads * 2;
+  int64_t i = (static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x) * 2;
+  for (; i + 1 < n; i += stride) {  // two points per 256-bit access
+    Point2 v = LoadPoint2<0>(in + i);
+    if constexpr (DESKEW) {
+      v.a = DeskewPoint<MODE>(v.a, P);
+      v.b = DeskewPoint<MODE>(v.b, P);
+      if constexpr (WRITE_CLOUD) StorePoint2<0>(cloud_out + i, v);
+    }
+    Point2 r;
+    r.a = ProjectPoint(v.a, K);
+    r.b = ProjectPoint(v.b, K);
+    StorePoint2<0>(pix_out + i, r);
+  }
+  if (i < n) {  // odd tail
+    float4 p = LoadPoint<0>(in + i);
+    if constexpr (DESKEW) {
+      p = DeskewPoint<MODE>(p, P);
+      if constexpr (WRITE_CLOUD) StorePoint<0>(cloud_out + i, p);
+    }
+    StorePoint<0>(pix_out + i, ProjectPoint(p, K));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // GetPseudoTimeStamps (timestamp_mocking.cpp:56-63) in double, for callers that want the stamps themselves.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlockThreads)
@@ -536,6 +594,42 @@ cudaError_t LaunchDeskewBatch(const float* in, float* out, const int64_t* offset
                                                      n_batch_points, cfg, sm_count, stream);
   return DispatchBatch<KMC_B200_TIME_FROM_W>(in, out, offsets_dev, params_dev, n_frames, n_points, point_base,
                                              n_batch_points, cfg, sm_count, stream);
+}
+
+namespace {
+template <bool DESKEW, bool WRITE_CLOUD, int MODE>
+cudaError_t LaunchProjectT(const float* in, float* cloud_out, float* pix_out, int64_t n, const kmc_b200_frame_params& P,
+                           const kmc_b200_camera_params& K, bool vec2, int sm_count, cudaStream_t stream) {
+  int64_t const per_cta = static_cast<int64_t>(kBlockThreads) * (vec2 ? 2 : 1);
+  int64_t grid = (n + per_cta - 1) / per_cta;
+  int64_t const cap = static_cast<int64_t>(sm_count) * 5;
+  if (grid > cap) grid = cap;
+  auto const* in4 = reinterpret_cast<const float4*>(in);
+  auto* cloud4 = reinterpret_cast<float4*>(cloud_out);
+  auto* pix4 = reinterpret_cast<float4*>(pix_out);
+  if (vec2)
+    ProjectFrameKernel<DESKEW, WRITE_CLOUD, MODE, true><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(in4, cloud4, pix4, n, P, K);
+  else
+    ProjectFrameKernel<DESKEW, WRITE_CLOUD, MODE, false><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(in4, cloud4, pix4, n, P, K);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t LaunchProject(const float* in, float* cloud_out, float* pix_out, int64_t n, const kmc_b200_frame_params* params,
+                          const kmc_b200_camera_params& camera, int mode, bool vec2, int sm_count, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (!params) {
+    kmc_b200_frame_params const none{};
+    return LaunchProjectT<false, false, 0>(in, nullptr, pix_out, n, none, camera, vec2, sm_count, stream);
+  }
+  bool const az = (mode == KMC_B200_TIME_FROM_AZIMUTH);
+  if (cloud_out) {
+    return az ? LaunchProjectT<true, true, KMC_B200_TIME_FROM_AZIMUTH>(in, cloud_out, pix_out, n, *params, camera, vec2, sm_count, stream)
+              : LaunchProjectT<true, true, KMC_B200_TIME_FROM_W>(in, cloud_out, pix_out, n, *params, camera, vec2, sm_count, stream);
+  }
+  return az ? LaunchProjectT<true, false, KMC_B200_TIME_FROM_AZIMUTH>(in, nullptr, pix_out, n, *params, camera, vec2, sm_count, stream)
+            : LaunchProjectT<true, false, KMC_B200_TIME_FROM_W>(in, nullptr, pix_out, n, *params, camera, vec2, sm_count, stream);
 }
 
 cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,

@@ -33,6 +33,11 @@ cudaError_t LaunchDeskewBatch(const float* in, float* out, const int64_t* offset
                               int64_t point_base, int64_t n_batch_points, int mode, const LaunchConfig& cfg, int sm_count,
                               cudaStream_t stream);
 
+// Projection onto one rectified camera, optionally fused behind the deskew (params != nullptr) and optionally also
+// writing the deskewed cloud (cloud_out != nullptr).
+cudaError_t LaunchProject(const float* in, float* cloud_out, float* pix_out, int64_t n, const kmc_b200_frame_params* params,
+                          const kmc_b200_camera_params& camera, int mode, bool vec2, int sm_count, cudaStream_t stream);
+
 cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,
                                    cudaStream_t stream);
 

@@ -247,5 +247,23 @@ def timed_frames(xyzi_f32, points_per_frame, T_start, T_end, stamps3, n_threads)
     return sec, chk.value
 
 
+def project_pointcloud(cloud_n4, tf_c00_lo, R_rect_00, P_rect_3x4, max_range=15.0):
+    """camera_model.cpp:5-36,38-95 for one camera, without the drawing.  Returns (uv (n,2), valid (n,) bool,
+    color_scale (n,), xyz_rect (n,3))."""
+    cloud = np.asarray(cloud_n4, dtype=np.float64)
+    n = cloud.shape[0]
+    cm = _colmajor(cloud)
+    uv = np.empty((n, 2))
+    valid = np.empty(n, dtype=np.int32)
+    color = np.empty(n)
+    rect = np.empty((n, 3))
+    fn = lib().kmc_oracle_project_pointcloud
+    fn.argtypes = [_dp, C.c_int64, _dp, _dp, _dp, C.c_double, _dp, C.POINTER(C.c_int32), _dp, _dp]
+    fn.restype = None
+    fn(_ptr(cm), n, _ptr(_colmajor(tf_c00_lo)), _ptr(_colmajor(R_rect_00)), _ptr(_colmajor(P_rect_3x4)), max_range, _ptr(uv),
+       valid.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(color), _ptr(rect))
+    return uv, valid.astype(bool), color, rect
+
+
 def hardware_threads() -> int:
     return int(lib().kmc_oracle_hardware_threads())

@@ -492,6 +492,41 @@ static bool DeskewXyziScan(float const* xyzi, int64_t n, Affine const& T_start, 
   return ok;
 }
 
+// ---------- camera_model.cpp (the per-point part of the projection, without the cv::circle drawing) ----
+
+// camera_model.cpp:38-95 (ProjectPointcloudOnFrame) followed by :5-36 (ProjectPointcloudOnImage) for ONE camera:
+//   X_c00      = tf_c00_lo * (x y z 1)                      :63-75
+//   X_rect     = R_rect_00 * X_c00   (rotation as an Affine) :78-81
+//   pixels     = P_rect * X_rect ; pixels /= pixels.z        :9-12
+//   skip when z_rect < 0.01 or z_rect > max_range or y_rect > 1.25                :16-24
+//   color_scale = 255 * z_rect / (max_range - 0.01) ; cv::Point truncates u, v to int   :27-31
+// cloud is column-major n x 4 (the 4th column is ignored: the reference overwrites it with ones, :63-64).
+// P_rect is 3x4 column-major.  out: u, v (double, before the int truncation), valid (0/1), color_scale.
+static void ProjectPointcloud(double const* cloud, int64_t n, Affine const& tf_c00_lo, Mat3 const& R_rect_00, double const P[12],
+                              double max_range, double* uv, int32_t* valid, double* color_scale, double* xyz_rect) {
+  Affine R_rect = AffineIdentity();
+  R_rect.L = Mul(R_rect_00, R_rect.L);  // R_rect_00 = camera_00.R_rect * Identity  (:78-79)
+  R_rect.t = Mul(R_rect_00, R_rect.t);
+  for (int64_t i = 0; i < n; ++i) {
+    double const p[4] = {cloud[i], cloud[n + i], cloud[2 * n + i], 1.0};
+    double c00[4], rect[4];
+    AffineApply(tf_c00_lo, p, c00);
+    AffineApply(R_rect, c00, rect);
+    double pix[3];
+    for (int r = 0; r < 3; ++r) pix[r] = P[0 * 3 + r] * rect[0] + P[1 * 3 + r] * rect[1] + P[2 * 3 + r] * rect[2] + P[3 * 3 + r] * rect[3];
+    uv[2 * i + 0] = pix[0] / pix[2];
+    uv[2 * i + 1] = pix[1] / pix[2];
+    double const in_front = rect[2], below = rect[1];
+    valid[i] = !((in_front < 0.01) || (in_front > max_range) || (below > 1.25));
+    color_scale[i] = 255.0 * (in_front / (max_range - 0.01));
+    if (xyz_rect) {
+      xyz_rect[3 * i + 0] = rect[0];
+      xyz_rect[3 * i + 1] = rect[1];
+      xyz_rect[3 * i + 2] = rect[2];
+    }
+  }
+}
+
 }  // namespace kmc_oracle
 
 // ============================================================================================================
@@ -642,6 +677,14 @@ double kmc_oracle_timed_frames(float const* xyzi, int64_t points_per_frame, int3
   for (double p : partial) total += p;
   if (checksum) *checksum = total;
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// cloud column-major n x 4; tf 4x4, R_rect 3x3, P_rect 3x4 all column-major; xyz_rect may be NULL
+void kmc_oracle_project_pointcloud(double const* cloud_colmajor, int64_t n, double const tf_c00_lo[16], double const R_rect_00[9],
+                                   double const P_rect[12], double max_range, double* uv, int32_t* valid, double* color_scale,
+                                   double* xyz_rect) {
+  ProjectPointcloud(cloud_colmajor, n, FromColMajor16(tf_c00_lo), FromColMajor9(R_rect_00), P_rect, max_range, uv, valid, color_scale,
+                    xyz_rect);
 }
 
 int kmc_oracle_hardware_threads(void) { return static_cast<int>(std::thread::hardware_concurrency()); }

@@ -112,6 +112,33 @@ def main():
     med, best = time_launches(fn, reps=50, flush=flush)
     out["config5_dense_10m"] = {"points": n, "kernel_us_median": med * 1e3, "kernel_us_best": best * 1e3,
                                 "mpoints_per_s": n / (med * 1e-3) / 1e6, "gb_per_s_32B_per_point": 32 * n / (med * 1e-3) / 1e9}
+    # ---- projection onto a camera, standalone and fused behind the deskew (100 M points, 1.6 GB) ---
+    n = 100_000_000
+    del d_in, d_out
+    d_in = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(d_in.data_ptr(), n, 1, 128, 20110926, 0, stream)
+    d_out = torch.empty_like(d_in)
+    d_pix = torch.empty_like(d_in)
+    T = np.eye(4)
+    T[:3, :3] = np.array([7.533745e-03, -9.999714e-01, -6.166020e-04, 1.480249e-02, 7.280733e-04, -9.998902e-01, 9.998621e-01,
+                          7.523790e-03, 1.480755e-02]).reshape(3, 3)
+    T[:3, 3] = [-4.069766e-03, -7.631618e-02, -2.717806e-01]
+    R_rect = np.array([9.999239e-01, 9.837760e-03, -7.445048e-03, -9.869795e-03, 9.999421e-01, -4.278459e-03, 7.402527e-03,
+                       4.351614e-03, 9.999631e-01]).reshape(3, 3)
+    P2 = np.array([7.215377e+02, 0, 6.095593e+02, 4.485728e+01, 0, 7.215377e+02, 1.728540e+02, 2.163791e-01, 0, 0, 1, 2.745884e-03]).reshape(3, 4)
+    cam = capi.camera_params_from_calibration(P2, R_rect, T, 15.0)
+    proj = {}
+    for name, bpp, fn in (
+            ("deskew_only", 32, lambda: capi.deskew_frame_device(d_in.data_ptr(), d_out.data_ptr(), n, p, 0, stream)),
+            ("project_only", 32, lambda: capi.project_frame_device(d_in.data_ptr(), d_pix.data_ptr(), n, cam, stream)),
+            ("deskew_project_fused_cloud_and_pixels", 48,
+             lambda: capi.deskew_project_frame_device(d_in.data_ptr(), d_out.data_ptr(), d_pix.data_ptr(), n, p, cam, 0, stream)),
+            ("deskew_project_fused_pixels_only", 32,
+             lambda: capi.deskew_project_frame_device(d_in.data_ptr(), 0, d_pix.data_ptr(), n, p, cam, 0, stream))):
+        med, best = time_launches(fn, reps=20)
+        proj[name] = {"bytes_per_point": bpp, "kernel_us_median": med * 1e3, "mpoints_per_s": n / (med * 1e-3) / 1e6,
+                      "gb_per_s": bpp * n / (med * 1e-3) / 1e9}
+    out["projection_100m_points"] = proj
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/sweep.json")
+    ap.add_argument("--frame", action="store_true", help="time the single-frame kernel over the whole buffer instead of the batch kernel")
     ap.add_argument("--tunes", default=None, help="semicolon-separated KMC_B200_TUNE strings to time instead of the staged sweep")
     args = ap.parse_args()
     torch.cuda.set_device(0)
@@ -58,10 +59,15 @@ def main():
     print(f"torch copy_            median {gbs(med):8.1f} GB/s  best {gbs(best):8.1f} GB/s", flush=True)
     results.append({"shape": "torch.copy_", "median_gbs": gbs(med), "best_gbs": gbs(best)})
 
+    one = capi.FrameParams.from_buffer_copy(params[:1].tobytes())
+
     def run(tune):
         os.environ["KMC_B200_TUNE"] = tune
-        med, best = timed(lambda: capi.deskew_batch_device(d_in.data_ptr(), d_out.data_ptr(), d_off.data_ptr(), d_par.data_ptr(),
-                                                           args.scans, n, args.mode, stream))
+        if args.frame:
+            med, best = timed(lambda: capi.deskew_frame_device(d_in.data_ptr(), d_out.data_ptr(), n, one, args.mode, stream))
+        else:
+            med, best = timed(lambda: capi.deskew_batch_device(d_in.data_ptr(), d_out.data_ptr(), d_off.data_ptr(), d_par.data_ptr(),
+                                                               args.scans, n, args.mode, stream))
         print(f"{tune:48s} median {gbs(med):8.1f} GB/s  best {gbs(best):8.1f} GB/s", flush=True)
         results.append({"shape": tune, "median_gbs": gbs(med), "best_gbs": gbs(best)})
         return gbs(med)

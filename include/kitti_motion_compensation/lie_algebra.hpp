@@ -9,24 +9,24 @@
 
 namespace kmc::lie {
 
-Eigen::Matrix3d Hat(Eigen::Vector3d const& a);
+using Vec3 = Eigen::Vector3d;
+using Mat3 = Eigen::Matrix3d;
 
-Eigen::Vector3d Vee(Eigen::Matrix3d const& a);
+// skew-symmetric matrix of a 3-vector, and its inverse map
+Mat3 Hat(const Vec3& omega);
+Vec3 Vee(const Mat3& skew);
 
-// SO(3) exponential (Rodrigues)
-Eigen::Matrix3d Exp(Eigen::Vector3d const& phi);
+// SO(3): Rodrigues exponential and its logarithm
+Mat3 Exp(const Vec3& rotation_vector);
+Vec3 Log(const Mat3& rotation);
 
-// SO(3) logarithm
-Eigen::Vector3d Log(Eigen::Matrix3d const& R);
+// left Jacobian of SO(3) and its closed-form inverse
+Mat3 LeftJacobian(const Vec3& rotation_vector);
+Mat3 InverseLeftJacobian(const Vec3& rotation_vector);
 
-Eigen::Matrix3d LeftJacobian(Eigen::Vector3d const& phi);
-
-Eigen::Matrix3d InverseLeftJacobian(Eigen::Vector3d const& phi);
-
-// SE(3) exponential: rotation Exp(phi), translation J(phi) rho
-Eigen::Affine3d Exp(Twist const& xi);
-
-// SE(3) logarithm; the rotation is the polar projection of T's linear block, as Eigen's Affine-mode rotation()
-Twist Log(Eigen::Affine3d const& T);
+// SE(3): rotation Exp(phi), translation J(phi) rho  /  the inverse map.  Log takes the polar projection of the linear
+// block, exactly what Eigen's Affine-mode rotation() returns.
+Eigen::Affine3d Exp(const Twist& twist);
+Twist Log(const Eigen::Affine3d& transform);
 
 }  // namespace kmc::lie

@@ -2,7 +2,7 @@
 // (include/kitti_motion_compensation/motion_compensation.hpp:8-13, src/.../motion_compensation.cpp:9-28).
 //
 // MotionCompensateFrame maps every point, measured in the sensor frame at its own capture time, into the sensor frame
-// at `requested_time`:  p' = T(requested_time)^-1 T(t_i) p  with T(.) the constant-twist interpolation between
+// at the requested time:  p' = T(t_requested)^-1 T(t_i) p  with T(.) the constant-twist interpolation between
 // frame.T_start and frame.T_end.  Here it runs as ONE fused CUDA kernel on a B200 (libkmc_b200: float4 xyz + per-point
 // trajectory fraction in, float4 out); there is no CPU fallback — without a usable device it throws std::runtime_error.
 // Out-of-range times abort, as in the reference.  Coordinates are carried in float32 on the device: the result equals
@@ -16,14 +16,15 @@ namespace kmc {
 
 using TrajectoryInterpolator = trajectory_interpolation::TrajectoryInterpolator;
 
-// One point (host, double): correction = interpolator.RelativePoseBetweenTimes(requested_time, point_stamp); returns
-// correction * point.  Scalar convenience API; MotionCompensateFrame does not call it.
-Vector4d MotionCompensatePoint(TrajectoryInterpolator const& trajectory_interpolator, Time const point_stamp,
-                               Vector4d const& point, Time const requested_time);
+// One point (host, double): interpolator.RelativePoseBetweenTimes(t_requested, t_point) applied to xyz1.
+// Scalar convenience API; MotionCompensateFrame does not call it.
+Vector4d MotionCompensatePoint(const TrajectoryInterpolator& interpolator, const Time t_point, const Vector4d& xyz1,
+                               const Time t_requested);
 
-Pointcloud MotionCompensateFrame(Frame const& frame, Time const requested_time);
+// A whole scan (CUDA).
+Pointcloud MotionCompensateFrame(const Frame& frame, const Time t_requested);
 
 // Selects the CUDA device used by the calls above (default 0).  Addition of this implementation.
-void SetMotionCompensationDevice(int device);
+void SetMotionCompensationDevice(int device_ordinal);
 
 }  // namespace kmc

@@ -11,10 +11,13 @@
 
 namespace kmc {
 
-double FractionOfScanCompleted(Eigen::Vector4d const point);
+// in [0, 1]; 0.5 is straight ahead (the camera trigger direction)
+double FractionOfScanCompleted(const Eigen::Vector4d xyz1);
 
-Time GetPseudoTimeStamp(Eigen::Vector4d const point, Time const scan_start, Time const scan_end);
+// one point (host)
+Time GetPseudoTimeStamp(const Eigen::Vector4d xyz1, const Time t_scan_begin, const Time t_scan_finish);
 
-VectorXd GetPseudoTimeStamps(Pointcloud const &cloud, Time const start_time, Time const end_time);
+// every row of the cloud (CUDA)
+VectorXd GetPseudoTimeStamps(const Pointcloud& xyz1_rows, const Time t_scan_begin, const Time t_scan_finish);
 
 }  // namespace kmc

@@ -13,24 +13,22 @@
 
 namespace kmc::trajectory_interpolation {
 
-Affine3d InterpolateTrajectory(Oxts const &odometry_1, Oxts const &odometry_2, Time const time);
+// pose at `t` on the screw motion between two OxTS packets (poses from OxtsToPose, times from their stamps)
+Affine3d InterpolateTrajectory(const Oxts& packet_a, const Oxts& packet_b, const Time t);
 
 class TrajectoryInterpolator {
  public:
-  // poses from OxtsToPose(odometry_k), times from odometry_k.stamp
-  TrajectoryInterpolator(Oxts const &odometry_1, Oxts const &odometry_2);
+  TrajectoryInterpolator(const Oxts& packet_a, const Oxts& packet_b);
+  TrajectoryInterpolator(const Time t_a, const Affine3d& pose_a, const Time t_b, const Affine3d& pose_b);
 
-  TrajectoryInterpolator(Time const time_1, Affine3d const &pose_1, Time const time_2, Affine3d const &pose_2);
+  Affine3d GetPoseAtTime(const Time t) const;
+  Affine3d RelativePoseBetweenTimes(const Time t_anchor, const Time t_query) const;
 
-  Affine3d GetPoseAtTime(Time const time) const;
-
-  Affine3d RelativePoseBetweenTimes(Time const anchor_time, Time const query_time) const;
-
-  // additions of this implementation (read-only accessors used by the batched deskew entry points)
+  // additions of this implementation: read-only access for the batched entry points
   Time time_1() const { return time_1_; }
   Time time_2() const { return time_2_; }
-  Affine3d const &pose_1() const { return pose_1_; }
-  Affine3d const &pose_2() const { return pose_2_; }
+  const Affine3d& pose_1() const { return pose_1_; }
+  const Affine3d& pose_2() const { return pose_2_; }
 
  private:
   Time time_1_;

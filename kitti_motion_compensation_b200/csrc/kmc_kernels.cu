@@ -544,16 +544,18 @@ uint64_t LaunchCount() { return g_launches.load(std::memory_order_relaxed); }
 
 LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_count) {
   // Defaults from the B200 sweeps (profiles/r01_sweep_*.log): one 256-bit load + one 256-bit store per thread per tile,
-  // plain ld/st, 5 CTAs x 256 threads per SM (40 KB of loads in flight per SM), work items of 8 tiles.  The optimum is
-  // sharp: 3 / 4 / 5 / 6 CTAs per SM measured 5.8 / 6.35 / 6.5 / 6.05 TB/s, and more bytes in flight per thread
-  // (2-4 loads) measured 5.9-6.1 TB/s — at the copy ceiling extra requests only lengthen the DRAM queues.
+  // plain ld/st, 9 CTAs x 128 threads per SM (1152 threads, 36 KB of loads in flight per SM), work items of 16 tiles
+  // (4096 points).  The optimum is sharp in resident threads per SM: 768 / 1024 / 1152 / 1280 / 1408 / 1536 threads
+  // measured 5.8 / 6.39 / 6.54 / 6.50 / 6.14 / 6.05 TB/s (interleaved A/B runs, profiles/r01_sweep_ab.log), and more
+  // bytes in flight per thread (2-4 loads) measured 5.9-6.1 TB/s — at the copy ceiling extra requests only lengthen
+  // the DRAM queues.
   LaunchConfig cfg;
   cfg.vec = 2;
   cfg.unroll = 1;
   cfg.hint = 0;
-  cfg.block = 256;
-  cfg.ctas_per_sm = 5;
-  cfg.item_tiles = 8;
+  cfg.block = 128;
+  cfg.ctas_per_sm = 9;
+  cfg.item_tiles = 16;
   // Mid-size inputs: keep >= 16 work items per resident CTA so the tail stays small; tiny inputs (latency bound):
   // one tile per item and 128-bit accesses to spread over as many CTAs as possible.
   int64_t const tile = static_cast<int64_t>(cfg.block) * cfg.unroll * cfg.vec;

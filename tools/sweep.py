@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     ap.add_argument("--frame", action="store_true", help="time the single-frame kernel over the whole buffer instead of the batch kernel")
+    ap.add_argument("--rounds", type=int, default=1, help="with --tunes: interleave the shapes this many times (A/B/A/B)")
     ap.add_argument("--tunes", default=None, help="semicolon-separated KMC_B200_TUNE strings to time instead of the staged sweep")
     args = ap.parse_args()
     torch.cuda.set_device(0)
@@ -72,7 +73,16 @@ def main():
         results.append({"shape": tune, "median_gbs": gbs(med), "best_gbs": gbs(best)})
         return gbs(med)
 
-    if args.tunes:
+    if args.tunes and args.rounds > 1:
+        # A/B/A/B: the shapes take turns so that box-to-box and thermal drift hit all of them alike
+        table = {t.strip(): [] for t in args.tunes.split(";")}
+        for _ in range(args.rounds):
+            for tune in table:
+                table[tune].append(run(tune))
+        for tune, vals in table.items():
+            print(f"ROUNDS {tune:52s} mean {statistics.fmean(vals):8.1f}  min {min(vals):8.1f}  max {max(vals):8.1f} GB/s", flush=True)
+        args.staged = False
+    elif args.tunes:
         for tune in args.tunes.split(";"):
             run(tune.strip())
         args.staged = False

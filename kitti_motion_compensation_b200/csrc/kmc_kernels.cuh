@@ -17,6 +17,9 @@ struct LaunchConfig {
   int block;       // threads per CTA (128, 256, 512)
   int ctas_per_sm; // persistent grid = SMs * ctas_per_sm (capped by the number of work items)
   int item_tiles;  // tiles per work item (a work item is the unit a CTA takes per scheduling step)
+  int bulk;        // 1 = single-frame kernel variant staged through shared memory by the TMA engine (kmc_kernels_bulk.cu);
+                   //     `unroll` then means points per thread per stage (2, 4, 8)
+  int stages;      // shared-memory slots of the bulk variant (3, 4)
 };
 
 constexpr int kBlockThreads = 256;
@@ -32,6 +35,14 @@ cudaError_t LaunchDeskewBatch(const float* in, float* out, const int64_t* offset
                               const kmc_b200_frame_params* params_dev, int32_t n_frames, int64_t n_points,
                               int64_t point_base, int64_t n_batch_points, int mode, const LaunchConfig& cfg, int sm_count,
                               cudaStream_t stream);
+
+// Single-frame deskew staged through shared memory with cp.async.bulk (measured alternative, see kmc_kernels_bulk.cu).
+cudaError_t LaunchDeskewFrameBulk(const float* in, float* out, int64_t n, const kmc_b200_frame_params& P, int mode, int block,
+                                  int pts_per_thread, int stages, int ctas_per_sm, int sm_count, cudaStream_t stream);
+
+cudaError_t LaunchDeskewBatchBulk(const float* in, float* out, const int64_t* offsets, const kmc_b200_frame_params* table,
+                                  int32_t n_frames, int64_t n, int64_t point_base, int64_t n_batch_points, int mode, int block,
+                                  int pts_per_thread, int stages, int ctas_per_sm, int sm_count, cudaStream_t stream);
 
 // Projection onto one rectified camera, optionally fused behind the deskew (params != nullptr) and optionally also
 // writing the deskewed cloud (cloud_out != nullptr).

@@ -520,3 +520,39 @@ def test_device_entry_points_capture_into_a_cuda_graph(capi, cuda):
         pts = d_in[f * n:(f + 1) * n].cpu().numpy()
         cf = helpers.closed_form_deskew(pts, xi[f], 0.5)
         assert np.abs(replayed[f * n:(f + 1) * n, :3].cpu().numpy() - cf).max() < TOL_M
+
+
+@pytest.mark.parametrize("tune", ["bulk=1,block=128,unroll=2,stages=4,ctas=8", "bulk=1,block=256,unroll=4,stages=4,ctas=3",
+                                  "bulk=1,block=256,unroll=8,stages=3,ctas=2", "bulk=1,block=128,unroll=4,stages=3,ctas=6"])
+@pytest.mark.parametrize("n", [1, 5_000, 130_000, 1_000_003])
+def test_tma_bulk_staged_variant_matches_register_path_bitwise(capi, cuda, monkeypatch, tune, n):
+    """The cp.async.bulk (TMA engine) + mbarrier staged single-frame kernel computes the same bits as the default."""
+    pts = helpers.synthetic_scan(n, 64, 11)
+    p = capi.frame_params_from_twist(helpers.CONFIG1_TWIST, 0.4)
+    monkeypatch.delenv("KMC_B200_TUNE", raising=False)
+    want = run_frame(cuda, capi, pts, p)
+    monkeypatch.setenv("KMC_B200_TUNE", tune)
+    got = run_frame(cuda, capi, pts, p)
+    assert got.tobytes() == want.tobytes()
+    got_w = run_frame(cuda, capi, pts, p, mode=capi.TIME_FROM_W)
+    monkeypatch.delenv("KMC_B200_TUNE")
+    assert got_w.tobytes() == run_frame(cuda, capi, pts, p, mode=capi.TIME_FROM_W).tobytes()
+
+
+@pytest.mark.parametrize("tune", ["bulk=1,block=256,unroll=4,stages=2,ctas=2", "bulk=1,block=128,unroll=2,stages=3,ctas=4",
+                                  "bulk=1,block=256,unroll=2,stages=4,ctas=2", "bulk=1,block=256,unroll=8,stages=2,ctas=1"])
+def test_batch_tma_bulk_variant_matches_register_path_bitwise(capi, oracle, cuda, monkeypatch, tune):
+    """The batch kernel staged by the TMA engine (points + per-frame records bulk-loaded into shared memory on one
+    mbarrier) against the register-path kernel: uniform tiles, tiles crossing one frame boundary, tiles covering many
+    tiny / empty frames, a partial last tile, and chunked launches with a point_base (host entry point)."""
+    sizes = [1000, 0, 1, 3, 2047, 2048, 2049, 0, 0, 5, 30_001, 17, 70_000, 2, 9_999, 0, 130_000, 130_000, 7]
+    pts, offsets, frames = make_batch(oracle, sizes, 700)
+    params = batch_params(capi, frames)
+    monkeypatch.delenv("KMC_B200_TUNE", raising=False)
+    want = run_batch(cuda, capi, pts, offsets, params)
+    want_w = run_batch(cuda, capi, pts, offsets, params, mode=capi.TIME_FROM_W)
+    monkeypatch.setenv("KMC_B200_TUNE", tune)
+    assert run_batch(cuda, capi, pts, offsets, params).tobytes() == want.tobytes()
+    assert run_batch(cuda, capi, pts, offsets, params, mode=capi.TIME_FROM_W).tobytes() == want_w.tobytes()
+    with capi.Handle(0, 50_000) as h:  # chunks of 50 000 points: every launch has a different point_base
+        assert h.deskew_batch(pts, offsets, params).tobytes() == want.tobytes()

@@ -54,6 +54,27 @@ int SmCount(int device, int* out) {
   return KMC_B200_OK;
 }
 
+// Makes `device` current for the scope and restores the caller's device afterwards (handles may live on any device).
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&previous_) != cudaSuccess) previous_ = -1;
+    status_ = (previous_ == device) ? cudaSuccess : cudaSetDevice(device);
+    changed_ = (status_ == cudaSuccess && previous_ != device);
+  }
+  ~DeviceGuard() {
+    if (changed_ && previous_ >= 0) cudaSetDevice(previous_);
+  }
+  DeviceGuard(DeviceGuard const&) = delete;
+  DeviceGuard& operator=(DeviceGuard const&) = delete;
+  cudaError_t status() const { return status_; }
+
+ private:
+  int previous_ = -1;
+  bool changed_ = false;
+  cudaError_t status_ = cudaSuccess;
+};
+
 bool ValidMode(int mode) { return mode == KMC_B200_TIME_FROM_AZIMUTH || mode == KMC_B200_TIME_FROM_W; }
 bool Aligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
@@ -109,7 +130,7 @@ namespace {
 
 void FreeHandle(kmc_b200_handle* h) {
   if (!h) return;
-  if (h->device >= 0) cudaSetDevice(h->device);
+  DeviceGuard const guard(h->device >= 0 ? h->device : 0);
   for (int s = 0; s < kmc_b200_handle::kSlots; ++s) {
     if (h->d_in[s]) cudaFree(h->d_in[s]);
     if (h->d_out[s]) cudaFree(h->d_out[s]);
@@ -141,7 +162,24 @@ int EnsureTables(kmc_b200_handle* h, int64_t n_frames) {
 // unstage, three slots deep so the copy engines and the SMs overlap.  `launch(slot, chunk_first_point, chunk_points)`
 // enqueues the kernel for a chunk on h->stream[slot].
 template <class Launch>
+int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch);
+
+// On any failure the slots' streams are drained before returning, so that no copy is still reading or writing the
+// caller's buffers after the call has reported an error.
+template <class Launch>
 int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
+  int const rc = StreamThroughDeviceImpl(h, in, out, n, launch);
+  if (rc != KMC_B200_OK) {
+    std::string const keep = t_last_error;
+    for (int s = 0; s < kmc_b200_handle::kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
+    cudaGetLastError();
+    t_last_error = keep;
+  }
+  return rc;
+}
+
+template <class Launch>
+int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
   constexpr int kSlots = kmc_b200_handle::kSlots;
   bool const in_pinned = IsPinnedHost(in);
   bool const out_pinned = IsPinnedHost(out);
@@ -450,7 +488,8 @@ int kmc_b200_handle_create(int device, int64_t capacity_points, kmc_b200_handle*
   auto* h = new kmc_b200_handle;
   h->device = device;
   h->capacity = (capacity_points + 7) & ~int64_t{7};  // even point count per chunk keeps 256-bit accesses aligned
-  cudaError_t e = cudaSetDevice(device);
+  DeviceGuard const guard(device);
+  cudaError_t e = guard.status();
   int rc = (e == cudaSuccess) ? SmCount(device, &h->sm_count) : FailCuda(e, "cudaSetDevice");
   size_t const bytes = static_cast<size_t>(h->capacity) * 16;
   for (int s = 0; s < kmc_b200_handle::kSlots && rc == KMC_B200_OK; ++s) {
@@ -502,7 +541,8 @@ int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, 
   if (n == 0) return KMC_B200_OK;
   if (!in || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_host: null point buffer");
   std::lock_guard<std::mutex> lock(h->mu);
-  KMC_CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
   kmc_b200_frame_params const P = *params;
   return StreamThroughDevice(h, in, out, n, [&](int slot, int64_t, int64_t count) -> int {
     auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
@@ -523,7 +563,8 @@ int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* in, float* out, 
   if (n_total == 0) return KMC_B200_OK;
   if (!in || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_host: null point buffer");
   std::lock_guard<std::mutex> lock(h->mu);
-  KMC_CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
   if (int rc = EnsureTables(h, n_frames)) return rc;
   // tables go up once, on slot 0's stream; the other slots wait for them through an event
   KMC_CUDA_TRY(cudaMemcpyAsync(h->d_offsets, offsets, static_cast<size_t>(n_frames + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream[0]));
@@ -579,7 +620,8 @@ int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, con
   if (n == 0) return KMC_B200_OK;
   if (!x || !y || !stamps) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_xy_host: null argument");
   std::lock_guard<std::mutex> lock(h->mu);
-  KMC_CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
   double* d = nullptr;  // x | y | stamps
   size_t const bytes = static_cast<size_t>(n) * sizeof(double);
   KMC_CUDA_TRY(cudaMalloc(&d, 3 * bytes));

@@ -404,25 +404,35 @@ cudaError_t DispatchBatch(const float* in, float* out, const int64_t* offsets, c
 #undef KMC_BATCH_CALL
 }
 
+// KMC_B200_TUNE="key=value,key=value,...": experiment knob for tools/sweep.py.  Parsed without strtok (re-entrant: the
+// multi-GPU entry point calls this from several host threads).
 void ApplyTuneEnv(LaunchConfig& cfg) {
   const char* env = std::getenv("KMC_B200_TUNE");
   if (!env || !*env) return;
-  char buf[256];
-  std::strncpy(buf, env, sizeof(buf) - 1);
-  buf[sizeof(buf) - 1] = 0;
-  for (char* tok = std::strtok(buf, ","); tok; tok = std::strtok(nullptr, ",")) {
-    char* eq = std::strchr(tok, '=');
-    if (!eq) continue;
-    *eq = 0;
-    int const v = std::atoi(eq + 1);
-    if (!std::strcmp(tok, "vec")) cfg.vec = v;
-    else if (!std::strcmp(tok, "unroll")) cfg.unroll = v;
-    else if (!std::strcmp(tok, "hint")) cfg.hint = v;
-    else if (!std::strcmp(tok, "ctas")) cfg.ctas_per_sm = v;
-    else if (!std::strcmp(tok, "item_tiles")) cfg.item_tiles = v;
-    else if (!std::strcmp(tok, "block")) cfg.block = v;
-    else if (!std::strcmp(tok, "bulk")) cfg.bulk = v;
-    else if (!std::strcmp(tok, "stages")) cfg.stages = v;
+  const char* p = env;
+  while (*p) {
+    const char* key = p;
+    while (*p && *p != '=' && *p != ',') ++p;
+    size_t const key_len = static_cast<size_t>(p - key);
+    int value = 0;
+    bool has_value = false;
+    if (*p == '=') {
+      ++p;
+      value = std::atoi(p);
+      has_value = true;
+      while (*p && *p != ',') ++p;
+    }
+    if (*p == ',') ++p;
+    if (!has_value) continue;
+    auto is = [&](const char* name) { return std::strlen(name) == key_len && std::strncmp(key, name, key_len) == 0; };
+    if (is("vec")) cfg.vec = value;
+    else if (is("unroll")) cfg.unroll = value;
+    else if (is("hint")) cfg.hint = value;
+    else if (is("ctas")) cfg.ctas_per_sm = value;
+    else if (is("item_tiles")) cfg.item_tiles = value;
+    else if (is("block")) cfg.block = value;
+    else if (is("bulk")) cfg.bulk = value;
+    else if (is("stages")) cfg.stages = value;
   }
 }
 

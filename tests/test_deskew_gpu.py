@@ -556,3 +556,32 @@ def test_batch_tma_bulk_variant_matches_register_path_bitwise(capi, oracle, cuda
     assert run_batch(cuda, capi, pts, offsets, params, mode=capi.TIME_FROM_W).tobytes() == want_w.tobytes()
     with capi.Handle(0, 50_000) as h:  # chunks of 50 000 points: every launch has a different point_base
         assert h.deskew_batch(pts, offsets, params).tobytes() == want.tobytes()
+
+
+def test_entry_points_are_reentrant_across_host_threads(capi, oracle, cuda):
+    """The reference's MotionCompensateFrame touches only its arguments (re-entrant).  Here: four host threads, each with
+    its own handle (own streams and staging), hammer the host entry point concurrently; every result must equal the
+    single-threaded one.  ctypes releases the GIL during the calls, so they really overlap."""
+    import threading
+    sizes = [40_000 + 1_111 * k for k in range(8)]
+    pts, offsets, frames = make_batch(oracle, sizes, 800)
+    params = batch_params(capi, frames)
+    want = run_batch(cuda, capi, pts, offsets, params)
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            with capi.Handle(0, 30_000 + 1_000 * tid) as h:
+                for _ in range(5):
+                    results[tid] = h.deskew_batch(pts, offsets, params)
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for tid in range(4):
+        assert results[tid].tobytes() == want.tobytes(), f"thread {tid}"

@@ -95,6 +95,20 @@ def build_cpp_test(name: str, force: bool = False) -> str:
     return out
 
 
+def build_example(force: bool = False) -> str:
+    """examples/motion_compensate_runs.cpp -> kitti_motion_compensation_b200/lib/motion_compensate_runs"""
+    build_dropin()
+    src = os.path.join(REPO_DIR, "examples", "motion_compensate_runs.cpp")
+    out = os.path.join(LIB_DIR, "motion_compensate_runs")
+    if not force and not _stale(out, [src, DROPIN_LIB_PATH]):
+        return out
+    cmd = [_cxx(), "-std=c++17", "-O2", "-Wall", "-I", os.path.join(REPO_DIR, "include"), "-o", out, src,
+           "-L", LIB_DIR, "-lkitti_motion_compensation_lib", "-lkmc_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_dropin(force="--force" in sys.argv))
+    print(build_example(force="--force" in sys.argv))

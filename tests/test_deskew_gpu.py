@@ -585,3 +585,42 @@ def test_entry_points_are_reentrant_across_host_threads(capi, oracle, cuda):
     assert not errors, errors
     for tid in range(4):
         assert results[tid].tobytes() == want.tobytes(), f"thread {tid}"
+
+
+def test_more_than_2_to_31_points(capi, cuda):
+    """Maximum sizes: 64-bit point indexing end to end.  One frame of 2^31 + 12 345 points (34 GB in, 34 GB out) through the
+    single-frame kernel, then the same buffer as a two-frame batch whose boundary lies beyond 2^31 (odd offset)."""
+    torch = cuda
+    n = (1 << 31) + 12_345
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 2.2 * n * 16:
+        pytest.skip("not enough free device memory for the 2^31-point case")
+    stream = torch.cuda.current_stream().cuda_stream
+    d_in = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(d_in.data_ptr(), n, 1, 128, 99, 0, stream)
+    d_out = torch.zeros((n + 8, 4), dtype=torch.float32, device="cuda")
+    xi = np.array([2.0, 0.05, -0.02, 0.002, -0.003, 0.04])
+    p = capi.frame_params_from_twist(xi, 0.5)
+    capi.deskew_frame_device(d_in.data_ptr(), d_out.data_ptr(), n, p, 0, stream)
+    torch.cuda.synchronize()
+    assert float(d_out[n:].abs().max()) == 0.0, "wrote past the end"
+    for lo, hi in ((0, 4096), ((1 << 31) - 2048, (1 << 31) + 2048), (n - 4096, n)):
+        pts = d_in[lo:hi].cpu().numpy()
+        got = d_out[lo:hi].cpu().numpy()
+        assert np.abs(got[:, :3] - helpers.closed_form_deskew(pts, xi, 0.5)).max() < TOL_M
+        assert np.array_equal(got[:, 3], pts[:, 3])
+    # two frames, boundary at 2^31 + 1 (beyond int32, odd): second frame moves the other way
+    cut = (1 << 31) + 1
+    params = capi.params_array([p, capi.frame_params_from_twist(-xi, 0.5)])
+    d_off = torch.tensor([0, cut, n], dtype=torch.int64, device="cuda")
+    d_par = dev(torch, params.view(np.uint8))
+    d_out.zero_()
+    capi.deskew_batch_device(d_in.data_ptr(), d_out.data_ptr(), d_off.data_ptr(), d_par.data_ptr(), 2, n, 0, stream)
+    torch.cuda.synchronize()
+    assert float(d_out[n:].abs().max()) == 0.0
+    a = d_in[cut - 1000:cut].cpu().numpy()
+    b = d_in[cut:cut + 1000].cpu().numpy()
+    assert np.abs(d_out[cut - 1000:cut, :3].cpu().numpy() - helpers.closed_form_deskew(a, xi, 0.5)).max() < TOL_M
+    assert np.abs(d_out[cut:cut + 1000, :3].cpu().numpy() - helpers.closed_form_deskew(b, -xi, 0.5)).max() < TOL_M
+    tail = d_in[n - 1000:n].cpu().numpy()
+    assert np.abs(d_out[n - 1000:n, :3].cpu().numpy() - helpers.closed_form_deskew(tail, -xi, 0.5)).max() < TOL_M

@@ -188,3 +188,46 @@ def test_oracle_digest_unchanged(oracle):
     idx = np.array(d["sample_index"])
     ref = oracle.deskew_xyzi_scan(pts[idx], T_start, T_end, t0, t2, t1)
     assert np.abs(ref[:, :3] - np.array(d["sample_xyz"])).max() < 1e-9
+
+
+def test_oracle_rotating_frames_against_matrix_exponential_in_40_digits(oracle):
+    """The reference ships no golden with rotation != 0.  Independent pin for rotating frames: the SE(3) closed forms the
+    reference uses (Rodrigues, left Jacobian and its inverse, lie_algebra.cpp:22-103) are the matrix exponential /
+    logarithm of 4x4 twist matrices, so  GetPoseAtTime(t) = P1 expm(x logm(P1^-1 P2))  can be evaluated with mpmath's
+    generic expm/logm at 40 digits — no Rodrigues, no Jacobians, no code shared with the oracle."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(2011)
+
+    def to_mp(a):
+        return mp.matrix([[mp.mpf(float(v)) for v in row] for row in np.asarray(a)])
+
+    for case in range(6):
+        P1 = helpers.random_pose(rng, mercator=bool(case % 2))
+        xi = helpers.random_twist(rng) * (1.0 if case < 4 else 6.0)  # up to ~0.3 rad per scan
+        P2 = P1 @ oracle.se3_exp(xi)
+        t1, t2 = 100.0, 100.1
+        M1, M2 = to_mp(P1), to_mp(P2)
+        L = mp.logm(mp.inverse(M1) * M2)
+        # lie::Log of the relative pose == the twist read off logm (rho in the last column, phi in the skew part)
+        xi_mp = [L[0, 3], L[1, 3], L[2, 3], L[2, 1], L[0, 2], L[1, 0]]
+        xi_or = oracle.se3_log(np.linalg.inv(P1) @ P2)
+        assert max(abs(float(a) - b) for a, b in zip(xi_mp, xi_or)) < 1e-9 * (1 if case % 2 == 0 else 100)  # Mercator: 6e6 m cancellation
+        for x in (0.0, 0.31, 0.5, 1.0):
+            want = M1 * mp.expm(mp.mpf(x) * L)
+            got = oracle.pose_at_time(t1, P1, t2, P2, t1 + x * (t2 - t1))
+            err_rot = max(abs(float(want[r, c]) - got[r, c]) for r in range(3) for c in range(3))
+            err_tr = max(abs(float(want[r, 3]) - got[r, 3]) for r in range(3))
+            assert err_rot < 1e-13
+            assert err_tr < (2e-8 if case % 2 else 1e-12)  # 1 ulp of a 6e6 m coordinate is 1e-9 m
+        # the deskew of points: T(x_req)^-1 T(x_i) p, with x_i from the azimuth
+        pts = helpers.synthetic_scan(24, 64, case)
+        x_req = 0.5
+        ref = oracle.deskew_xyzi_scan(pts, P1, P2, t1, t2, t1 + x_req * (t2 - t1))
+        for i in range(len(pts)):
+            x, y, z = (mp.mpf(float(v)) for v in pts[i, :3])
+            frac = (mp.pi - mp.atan2(y, x)) / (2 * mp.pi)
+            T = mp.expm((frac - mp.mpf(x_req)) * L)  # P1 cancels; exponentials of one generator commute
+            q = T * mp.matrix([x, y, z, 1])
+            err = max(abs(float(q[k]) - ref[i, k]) for k in range(3))
+            assert err < (5e-8 if case % 2 else 1e-11), (case, i, err)

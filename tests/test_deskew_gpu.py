@@ -624,3 +624,23 @@ def test_more_than_2_to_31_points(capi, cuda):
     assert np.abs(d_out[cut:cut + 1000, :3].cpu().numpy() - helpers.closed_form_deskew(b, -xi, 0.5)).max() < TOL_M
     tail = d_in[n - 1000:n].cpu().numpy()
     assert np.abs(d_out[n - 1000:n, :3].cpu().numpy() - helpers.closed_form_deskew(tail, -xi, 0.5)).max() < TOL_M
+
+
+@pytest.mark.parametrize("tune", [None, "bulk=1,block=256,unroll=4,stages=2,ctas=2"])
+@pytest.mark.parametrize("sizes", [[0, 0, 100, 0], [0, 5000, 0, 0], [3, 0, 0, 0, 0, 0, 0, 2], [0, 0, 0, 1], [1] * 300, [0, 1] * 200,
+                                   [2049, 0, 2047, 1, 1, 1, 4096, 4097]])
+def test_batch_with_leading_trailing_and_dense_empty_frames(capi, oracle, cuda, monkeypatch, tune, sizes):
+    pts, offsets, frames = make_batch(oracle, sizes, 900)
+    params = batch_params(capi, frames)
+    if tune is None:
+        monkeypatch.delenv("KMC_B200_TUNE", raising=False)
+    else:
+        monkeypatch.setenv("KMC_B200_TUNE", tune)
+    out = run_batch(cuda, capi, pts, offsets, params)
+    for f, (Ts, Te, xi, xr) in enumerate(frames):
+        a, b = offsets[f], offsets[f + 1]
+        if a == b:
+            continue
+        cf = helpers.closed_form_deskew(pts[a:b], xi, xr)
+        assert np.abs(out[a:b, :3] - cf).max() < TOL_M, f"frame {f}"
+    assert np.array_equal(out[:, 3], pts[:, 3])

@@ -3,10 +3,11 @@
 //
 // MotionCompensateFrame maps every point, measured in the sensor frame at its own capture time, into the sensor frame
 // at the requested time:  p' = T(t_requested)^-1 T(t_i) p  with T(.) the constant-twist interpolation between
-// frame.T_start and frame.T_end.  Here it runs as ONE fused CUDA kernel on a B200 (libkmc_b200: float4 xyz + per-point
-// trajectory fraction in, float4 out); there is no CPU fallback — without a usable device it throws std::runtime_error.
-// Out-of-range times abort, as in the reference.  Coordinates are carried in float32 on the device: the result equals
-// the reference's double result to < 1e-5 m for KITTI-range clouds (inputs loaded from .bin files are float32 anyway).
+// frame.T_start and frame.T_end.  Here it runs as ONE fused CUDA kernel on a B200, directly on the reference's layout
+// (column-major double cloud + per-point stamps in, column-major double cloud out; kmc_b200_deskew_cloud_f64_host);
+// there is no CPU fallback — without a usable device it throws std::runtime_error.  Out-of-range times abort, as in the
+// reference.  The per-point displacement is computed in fp32 and added to the double coordinate: the result equals
+// the reference's double result to ~2e-7 m for KITTI-range clouds.
 #pragma once
 
 #include "kitti_motion_compensation/data_types.hpp"

@@ -164,6 +164,15 @@ KMC_B200_API int kmc_b200_deskew_frame_device(const float* xyzi_in, float* xyzi_
 KMC_B200_API int kmc_b200_deskew_batch_device(const float* xyzi_in, float* xyzi_out, const int64_t* frame_offsets_dev,
                                  const kmc_b200_frame_params* params_dev, int32_t n_frames, int64_t n_points_total,
                                  int time_mode, void* stream);
+/* MotionCompensateFrame on the reference's OWN data layout (motion_compensation.cpp:16-28; data_types.hpp:14,58): the
+ * cloud and the result are COLUMN-major N x 4 doubles (Eigen::MatrixX4d::data()), stamps is the per-point time vector
+ * (LidarScan::timestamps).  The displacement is computed in fp32 and added to the double coordinate, so the result
+ * carries no float32 output rounding.  flags_dev (device int, caller-zeroed) receives bit 0 if any stamp lies outside
+ * [t_start, t_end] (where the reference asserts) and bit 1 if a 4th-column entry is not the homogeneous 1.  x_req =
+ * (t_req - t_start)/(t_end - t_start) must be the value params was built with. */
+KMC_B200_API int kmc_b200_deskew_cloud_f64_device(const double* cloud_colmajor, const double* stamps, double* out_colmajor,
+                                                  int64_t n_points, double t_start, double t_end, double t_req,
+                                                  const kmc_b200_frame_params* params_host, int* flags_dev, void* stream);
 /* GetPseudoTimeStamps (timestamp_mocking.cpp:56-63) on the device, double precision: stamps[i] =
  * start + frac(x_i, y_i) * (end - start). */
 KMC_B200_API int kmc_b200_pseudo_time_stamps_device(const float* xyzi_in, double* stamps_out, int64_t n_points, double scan_start,
@@ -217,6 +226,12 @@ KMC_B200_API int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* xyz
 KMC_B200_API int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_handles, const float* xyzi_in,
                                     float* xyzi_out, const int64_t* frame_offsets, const kmc_b200_frame_params* params,
                                     int32_t n_frames, int time_mode);
+/* The same from host memory (H2D + kernel + D2H on the handle's first stream).  Returns
+ * KMC_B200_ERR_TIME_OUT_OF_RANGE when a stamp was outside [t_start, t_end] and KMC_B200_ERR_BAD_SIZE when the 4th
+ * column is not all ones (the result is still written); *flags_out (optional) receives the raw bits. */
+KMC_B200_API int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud_colmajor, const double* stamps,
+                                                double* out_colmajor, int64_t n_points, double t_start, double t_end, double t_req,
+                                                const kmc_b200_frame_params* params, int* flags_out);
 /* GetPseudoTimeStamps on host columns x, y (length n each): H2D + kernel + D2H. */
 KMC_B200_API int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n_points,
                                                      double scan_start, double scan_end, double* stamps_out);

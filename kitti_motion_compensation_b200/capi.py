@@ -90,6 +90,8 @@ SIGNATURES = {
     "kmc_b200_project_frame_device": (C.c_int, [_vp, _vp, C.c_int64, C.POINTER(CameraParams), _vp]),
     "kmc_b200_deskew_project_frame_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(FrameParams), C.POINTER(CameraParams),
                                                        C.c_int, _vp]),
+    "kmc_b200_deskew_cloud_f64_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                                   C.POINTER(FrameParams), _vp, _vp]),
     "kmc_b200_pseudo_time_stamps_device": (C.c_int, [_vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_pseudo_time_stamps_xy_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_synth_scans_device": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, _vp]),
@@ -102,6 +104,8 @@ SIGNATURES = {
     "kmc_b200_deskew_frame_host": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(FrameParams), C.c_int]),
     "kmc_b200_deskew_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int]),
     "kmc_b200_deskew_batch_multi_gpu": (C.c_int, [C.POINTER(_vp), C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, C.c_int]),
+    "kmc_b200_deskew_cloud_f64_host": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                                 C.POINTER(FrameParams), C.POINTER(C.c_int)]),
     "kmc_b200_pseudo_time_stamps_xy_host": (C.c_int, [_vp, _dp, _dp, C.c_int64, C.c_double, C.c_double, _dp]),
     "kmc_b200_deskew_bin_file": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.POINTER(FrameParams), C.POINTER(C.c_int64)]),
 }
@@ -336,6 +340,17 @@ class Handle:
         offs = np.ascontiguousarray(offsets, dtype=np.int64)
         prm = np.ascontiguousarray(params, dtype=FRAME_PARAMS_DTYPE)
         check(lib().kmc_b200_deskew_batch_host(self._h, in_ptr, out_ptr, offs.ctypes.data, prm.ctypes.data, prm.size, mode))
+
+    def deskew_cloud_f64(self, cloud_n4: np.ndarray, stamps: np.ndarray, t_start: float, t_end: float, t_req: float,
+                         params: FrameParams):
+        """The reference's MotionCompensateFrame layout: (n,4) double cloud (x y z 1) + (n,) stamps -> ((n,4) double, flags, status)."""
+        cm = np.ascontiguousarray(np.asarray(cloud_n4, dtype=np.float64).T)  # column-major n x 4 == C-order 4 x n
+        ts = np.ascontiguousarray(stamps, dtype=np.float64)
+        out = np.empty_like(cm)
+        flags = C.c_int(0)
+        rc = lib().kmc_b200_deskew_cloud_f64_host(self._h, _ptr(cm), _ptr(ts), _ptr(out), ts.size, t_start, t_end, t_req,
+                                                  C.byref(params), C.byref(flags))
+        return out.T.copy(), flags.value, rc
 
     def pseudo_time_stamps(self, x: np.ndarray, y: np.ndarray, start: float, end: float) -> np.ndarray:
         xs = np.ascontiguousarray(x, dtype=np.float64)

@@ -123,6 +123,9 @@ struct kmc_b200_handle {
   int64_t* d_offsets = nullptr;
   kmc_b200_frame_params* d_params = nullptr;
   int64_t table_capacity = 0;  // frames
+  // scratch of the double-precision (reference layout) entry points, grown on demand and kept
+  double* d_f64 = nullptr;
+  size_t d_f64_bytes = 0;
   std::mutex mu;
 };
 
@@ -141,7 +144,19 @@ void FreeHandle(kmc_b200_handle* h) {
   }
   if (h->d_offsets) cudaFree(h->d_offsets);
   if (h->d_params) cudaFree(h->d_params);
+  if (h->d_f64) cudaFree(h->d_f64);
   delete h;
+}
+
+int EnsureF64Scratch(kmc_b200_handle* h, size_t bytes) {
+  if (bytes <= h->d_f64_bytes) return KMC_B200_OK;
+  if (h->d_f64) cudaFree(h->d_f64);
+  h->d_f64 = nullptr;
+  h->d_f64_bytes = 0;
+  size_t const want = bytes + bytes / 4;  // head room: clouds of a run differ by a few percent in size
+  KMC_CUDA_TRY(cudaMalloc(&h->d_f64, want));
+  h->d_f64_bytes = want;
+  return KMC_B200_OK;
 }
 
 int EnsureTables(kmc_b200_handle* h, int64_t n_frames) {
@@ -418,6 +433,24 @@ int kmc_b200_deskew_project_frame_device(const float* in, float* xyzi_out, float
   return ProjectCommon("deskew_project_frame_device", in, xyzi_out, uvzc_out, n, params, camera, mode, stream);
 }
 
+int kmc_b200_deskew_cloud_f64_device(const double* cloud, const double* stamps, double* out, int64_t n, double t_start, double t_end,
+                                     double t_req, const kmc_b200_frame_params* params, int* flags_dev, void* stream) {
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_cloud_f64_device: negative n_points");
+  if (!params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_device: null params");
+  if (!(t_end > t_start)) return Fail(KMC_B200_ERR_EMPTY_INTERVAL, "deskew_cloud_f64_device: t_end <= t_start");
+  if (!(t_req >= t_start && t_req <= t_end)) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "deskew_cloud_f64_device: requested time outside [t_start, t_end]");
+  if (n == 0) return KMC_B200_OK;
+  if (!cloud || !stamps || !out || !flags_dev) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_device: null buffer");
+  if (!Aligned(cloud, 8) || !Aligned(stamps, 8) || !Aligned(out, 8) || !Aligned(flags_dev, 4))
+    return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_cloud_f64_device: misaligned buffer");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewCloudF64(cloud, stamps, out, n, t_start, t_end, (t_req - t_start) / (t_end - t_start), *params,
+                                                   flags_dev, sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
 int kmc_b200_pseudo_time_stamps_device(const float* in, double* stamps, int64_t n, double start, double end, void* stream) {
   if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_device: negative n_points");
   if (n == 0) return KMC_B200_OK;
@@ -613,6 +646,42 @@ int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_h
   return KMC_B200_OK;
 }
 
+int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, const double* stamps, double* out, int64_t n, double t_start,
+                                   double t_end, double t_req, const kmc_b200_frame_params* params, int* flags_out) {
+  if (flags_out) *flags_out = 0;
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null handle");
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_cloud_f64_host: negative n_points");
+  if (!params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null params");
+  if (!(t_end > t_start)) return Fail(KMC_B200_ERR_EMPTY_INTERVAL, "deskew_cloud_f64_host: t_end <= t_start");
+  if (!(t_req >= t_start && t_req <= t_end)) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "deskew_cloud_f64_host: requested time outside [t_start, t_end]");
+  if (n == 0) return KMC_B200_OK;
+  if (!cloud || !stamps || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  size_t const col = static_cast<size_t>(n) * sizeof(double);
+  if (int rc = EnsureF64Scratch(h, 9 * col + 16)) return rc;
+  double* d = h->d_f64;  // cloud (4 columns) | stamps | result (4 columns) | flags
+  int* d_flags = reinterpret_cast<int*>(d + 9 * n);
+  cudaStream_t const st = h->stream[0];
+  int flags = 0;
+  cudaError_t e = cudaMemcpyAsync(d, cloud, 4 * col, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + 4 * n, stamps, col, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, sizeof(int), st);
+  if (e == cudaSuccess)
+    e = kmc_b200::dev::LaunchDeskewCloudF64(d, d + 4 * n, d + 5 * n, n, t_start, t_end, (t_req - t_start) / (t_end - t_start), *params, d_flags,
+                                            h->sm_count, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 5 * n, 4 * col, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaError_t const sync = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = sync;
+  if (e != cudaSuccess) return FailCuda(e, "deskew_cloud_f64_host");
+  if (flags_out) *flags_out = flags;
+  if (flags & 1) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "a point stamp lies outside [t_start, t_end] (reference asserts, trajectory_interpolation.cpp:32)");
+  if (flags & 2) return Fail(KMC_B200_ERR_BAD_SIZE, "the 4th cloud column must be the homogeneous 1 (data_types.hpp:13)");
+  return KMC_B200_OK;
+}
+
 int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n, double start, double end,
                                         double* stamps) {
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_xy_host: null handle");
@@ -622,16 +691,15 @@ int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, con
   std::lock_guard<std::mutex> lock(h->mu);
   DeviceGuard const guard(h->device);
   KMC_CUDA_TRY(guard.status());
-  double* d = nullptr;  // x | y | stamps
   size_t const bytes = static_cast<size_t>(n) * sizeof(double);
-  KMC_CUDA_TRY(cudaMalloc(&d, 3 * bytes));
+  if (int rc = EnsureF64Scratch(h, 3 * bytes)) return rc;
+  double* d = h->d_f64;  // x | y | stamps
   cudaStream_t const st = h->stream[0];
   cudaError_t e = cudaMemcpyAsync(d, x, bytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, y, bytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = kmc_b200::dev::LaunchPseudoTimeStampsXy(d, d + n, d + 2 * n, n, start, end, h->sm_count, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(stamps, d + 2 * n, bytes, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d);
   if (e != cudaSuccess) return FailCuda(e, "pseudo_time_stamps_xy_host");
   return KMC_B200_OK;
 }

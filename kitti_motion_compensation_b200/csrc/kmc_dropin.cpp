@@ -207,9 +207,10 @@ KMC_EXPORT Vector4d MotionCompensatePoint(TrajectoryInterpolator const& trajecto
   return correction * point;
 }
 
-// CUDA.  The reference's cloud is N x 4 column-major double with a homogeneous ones column and the per-point stamps
-// in scan.timestamps; the kernel wants interleaved float4.  The w lane carries each point's trajectory fraction
-// (KMC_B200_TIME_FROM_W), so whatever stamps the caller stored are honoured — not only azimuth-derived ones.
+// CUDA, on the reference's own layout: the column-major double cloud and the per-point stamp vector go to the device as
+// they are (kmc_b200_deskew_cloud_f64_host), the kernel forms each point's trajectory fraction from ITS stamp — whatever
+// the caller stored in scan.timestamps is honoured, not only azimuth-derived stamps — and adds the fp32 displacement to
+// the double coordinate.  No host-side layout conversion, no float32 rounding of the result.
 KMC_EXPORT Pointcloud MotionCompensateFrame(Frame const& frame, Time const requested_time) {
   Time const t1{frame.scan.stamp_start}, t2{frame.scan.stamp_end};
   Index const n{frame.scan.cloud.rows()};
@@ -218,7 +219,7 @@ KMC_EXPORT Pointcloud MotionCompensateFrame(Frame const& frame, Time const reque
   ToBuffer(frame.T_start, p1);
   ToBuffer(frame.T_end, p2);
   kmc_b200_frame_params params{};
-  int const rc = kmc_b200_frame_params_from_poses(p1, p2, t1, t2, requested_time, &params);
+  int rc = kmc_b200_frame_params_from_poses(p1, p2, t1, t2, requested_time, &params);
   if (rc == KMC_B200_ERR_TIME_OUT_OF_RANGE || rc == KMC_B200_ERR_EMPTY_INTERVAL) {
     if (n == 0 && rc == KMC_B200_ERR_TIME_OUT_OF_RANGE) return Pointcloud{MatrixX4d(0, 4)};  // the reference's loop never runs
     AbortOutOfRange("MotionCompensateFrame", requested_time, t1, t2);
@@ -229,29 +230,12 @@ KMC_EXPORT Pointcloud MotionCompensateFrame(Frame const& frame, Time const reque
   Pointcloud result{MatrixX4d(n, 4)};
   if (n == 0) return result;
 
-  const double* cloud = frame.scan.cloud.data();
-  const double* stamps = frame.scan.timestamps.data();
-  double const inv_duration = 1.0 / (t2 - t1);
-  std::vector<float> in(static_cast<size_t>(4 * n)), out(static_cast<size_t>(4 * n));
-  for (Index i = 0; i < n; ++i) {
-    double const t = stamps[i];
-    if (!(t >= t1 && t <= t2)) AbortOutOfRange("MotionCompensateFrame (point stamp)", t, t1, t2);
-    if (cloud[3 * n + i] != 1.0)
-      throw std::invalid_argument("MotionCompensateFrame: the 4th cloud column must be the homogeneous 1 (data_types.hpp:13)");
-    in[static_cast<size_t>(4 * i + 0)] = static_cast<float>(cloud[i]);
-    in[static_cast<size_t>(4 * i + 1)] = static_cast<float>(cloud[n + i]);
-    in[static_cast<size_t>(4 * i + 2)] = static_cast<float>(cloud[2 * n + i]);
-    in[static_cast<size_t>(4 * i + 3)] = static_cast<float>((t - t1) * inv_duration);
-  }
-  ThrowUnlessOk(kmc_b200_deskew_frame_host(DefaultHandle(), in.data(), out.data(), n, &params, KMC_B200_TIME_FROM_W),
-                "kmc_b200_deskew_frame_host");
-  double* res = result.data();
-  for (Index i = 0; i < n; ++i) {
-    res[i] = out[static_cast<size_t>(4 * i + 0)];
-    res[n + i] = out[static_cast<size_t>(4 * i + 1)];
-    res[2 * n + i] = out[static_cast<size_t>(4 * i + 2)];
-    res[3 * n + i] = 1.0;
-  }
+  int flags{0};
+  rc = kmc_b200_deskew_cloud_f64_host(DefaultHandle(), frame.scan.cloud.data(), frame.scan.timestamps.data(), result.data(), n, t1, t2,
+                                      requested_time, &params, &flags);
+  if (flags & 1) AbortOutOfRange("MotionCompensateFrame (a point stamp)", std::nan(""), t1, t2);  // GetPoseAtTime(point_stamp) asserts
+  if (flags & 2) throw std::invalid_argument("MotionCompensateFrame: the 4th cloud column must be the homogeneous 1 (data_types.hpp:13)");
+  ThrowUnlessOk(rc, "kmc_b200_deskew_cloud_f64_host");
   return result;
 }
 

@@ -52,6 +52,10 @@ cudaError_t LaunchProject(const float* in, float* cloud_out, float* pix_out, int
 cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,
                                    cudaStream_t stream);
 
+// Deskew in the reference's own layout: column-major N x 4 double cloud + per-point double stamps -> column-major double.
+cudaError_t LaunchDeskewCloudF64(const double* cloud, const double* stamps, double* out, int64_t n, double t1, double t2, double x_req,
+                                 const kmc_b200_frame_params& params, int* flags_dev, int sm_count, cudaStream_t stream);
+
 cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* stamps, int64_t n, double start, double end,
                                      int sm_count, cudaStream_t stream);
 

@@ -82,6 +82,29 @@ __device__ __forceinline__ void HalfAngleSC(float s, float x2, float& S, float& 
   C = 2.0f * hs * hs;
 }
 
+// Displacement of a point: delta = Exp(s xi) p - p, with s the signed fraction of the scan between the requested time and
+// the point's capture time (everything in fp32; see DESIGN.md §3 for why the displacement form).
+__device__ __forceinline__ float3 DeskewDelta(float x, float y, float z, float s, const kmc_b200_frame_params& P) {
+  float const s2 = s * s;
+  float S, C;
+  if (P.wide == 0.0f) {  // frame-uniform branch
+    SeriesSC(s, s2, s2 * P.theta2, S, C);
+  } else {
+    HalfAngleSC(s, s2 * P.theta2, S, C);
+  }
+  float const d = fmaf(P.phi[2], z, fmaf(P.phi[1], y, P.phi[0] * x));
+  // u = phi (phi.p) - th^2 p + phi x rho
+  float const ux = fmaf(P.phi[0], d, fmaf(-P.theta2, x, P.phi_x_rho[0]));
+  float const uy = fmaf(P.phi[1], d, fmaf(-P.theta2, y, P.phi_x_rho[1]));
+  float const uz = fmaf(P.phi[2], d, fmaf(-P.theta2, z, P.phi_x_rho[2]));
+  // v = phi x p + rho_perp
+  float const vx = fmaf(P.phi[1], z, fmaf(-P.phi[2], y, P.rho_perp[0]));
+  float const vy = fmaf(P.phi[2], x, fmaf(-P.phi[0], z, P.rho_perp[1]));
+  float const vz = fmaf(P.phi[0], y, fmaf(-P.phi[1], x, P.rho_perp[2]));
+  return make_float3(fmaf(C, ux, fmaf(S, vx, s * P.rho_par[0])), fmaf(C, uy, fmaf(S, vy, s * P.rho_par[1])),
+                     fmaf(C, uz, fmaf(S, vz, s * P.rho_par[2])));
+}
+
 template <int MODE>
 __device__ __forceinline__ float4 DeskewPoint(float4 p, const kmc_b200_frame_params& P) {
   float s;
@@ -91,26 +114,8 @@ __device__ __forceinline__ float4 DeskewPoint(float4 p, const kmc_b200_frame_par
   } else {
     s = p.w - P.x_req;
   }
-  float const s2 = s * s;
-  float S, C;
-  if (P.wide == 0.0f) {  // frame-uniform branch
-    SeriesSC(s, s2, s2 * P.theta2, S, C);
-  } else {
-    HalfAngleSC(s, s2 * P.theta2, S, C);
-  }
-  float const d = fmaf(P.phi[2], p.z, fmaf(P.phi[1], p.y, P.phi[0] * p.x));
-  // u = phi (phi.p) - th^2 p + phi x rho
-  float const ux = fmaf(P.phi[0], d, fmaf(-P.theta2, p.x, P.phi_x_rho[0]));
-  float const uy = fmaf(P.phi[1], d, fmaf(-P.theta2, p.y, P.phi_x_rho[1]));
-  float const uz = fmaf(P.phi[2], d, fmaf(-P.theta2, p.z, P.phi_x_rho[2]));
-  // v = phi x p + rho_perp
-  float const vx = fmaf(P.phi[1], p.z, fmaf(-P.phi[2], p.y, P.rho_perp[0]));
-  float const vy = fmaf(P.phi[2], p.x, fmaf(-P.phi[0], p.z, P.rho_perp[1]));
-  float const vz = fmaf(P.phi[0], p.y, fmaf(-P.phi[1], p.x, P.rho_perp[2]));
-  float const dx = fmaf(C, ux, fmaf(S, vx, s * P.rho_par[0]));
-  float const dy = fmaf(C, uy, fmaf(S, vy, s * P.rho_par[1]));
-  float const dz = fmaf(C, uz, fmaf(S, vz, s * P.rho_par[2]));
-  return make_float4(p.x + dx, p.y + dy, p.z + dz, p.w);
+  float3 const delta = DeskewDelta(p.x, p.y, p.z, s, P);
+  return make_float4(p.x + delta.x, p.y + delta.y, p.z + delta.z, p.w);  // one rounding at the magnitude of p
 }
 
 // ---------------------------------------------------------------------------------------------------------------

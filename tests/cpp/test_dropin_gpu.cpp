@@ -2,6 +2,7 @@
 // test/test_timestamp_mocking.cpp (whose fixture builds a Frame, i.e. runs GetPseudoTimeStamps), the loader/writer
 // round trip of test/test_data_io.cpp:115-149, and a whole MotionCompensateRun on a generated run folder —
 // all through this repository's drop-in headers, i.e. through the CUDA kernels.  argv[2] = path of the real scan.
+#include <chrono>
 #include <cstdlib>
 #include <filesystem>
 #include <fstream>
@@ -153,6 +154,15 @@ TEST(RealScanTest, LoadAndMotionCompensate) {
   }
   std::printf("    max |dxyz| vs double single-point path: %.3e m\n", worst);
   ASSERT_TRUE(worst < 1e-5);
+  // wall time of the reference-shaped call (H2D of the double cloud + stamps, kernel, D2H), after the warm-up above
+  auto const t_begin = std::chrono::steady_clock::now();
+  int const reps = 20;
+  for (int r = 0; r < reps; ++r) {
+    Pointcloud const again{MotionCompensateFrame(frame, middle)};
+    ASSERT_EQ(again.rows(), cloud.rows());
+  }
+  double const ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count() / reps;
+  std::printf("    kmc::MotionCompensateFrame(Frame, t): %.3f ms per 123 397-point frame = %.1f Mpoints/s\n", ms, 123397.0 / ms / 1e3);
 }
 
 // test/test_data_io.cpp:115-149 — write -> read round trip of the float32 xyzi format

@@ -644,3 +644,41 @@ def test_batch_with_leading_trailing_and_dense_empty_frames(capi, oracle, cuda, 
         cf = helpers.closed_form_deskew(pts[a:b], xi, xr)
         assert np.abs(out[a:b, :3] - cf).max() < TOL_M, f"frame {f}"
     assert np.array_equal(out[:, 3], pts[:, 3])
+
+
+def test_reference_layout_f64_entry_point(capi, oracle, cuda):
+    """kmc_b200_deskew_cloud_f64_host: MotionCompensateFrame on the reference's own layout (column-major double cloud +
+    per-point stamps).  The fp32 displacement is added to the DOUBLE coordinate, so there is no float32 output rounding:
+    the result is within ~1e-6 m of the reference's, and coordinates that are not float-representable stay exact."""
+    rng = np.random.default_rng(31)
+    pts = helpers.real_scan()
+    n = len(pts)
+    T_start, T_end, t0, t1, t2 = helpers.config1_frame()
+    cloud = np.concatenate([pts[:, :3].astype(np.float64), np.ones((n, 1))], axis=1)
+    cloud[:, :3] += rng.uniform(-1e-7, 1e-7, (n, 3))          # not representable in float32
+    stamps = oracle.pseudo_time_stamps(cloud, t0, t2)
+    stamps[:1000] = rng.uniform(t0, t2, 1000)                  # arbitrary stamps, not azimuth-derived
+    p = capi.frame_params_from_poses(T_start, T_end, t0, t2, t1)
+    with capi.Handle(0, 1024) as h:
+        out, flags, rc = h.deskew_cloud_f64(cloud, stamps, t0, t2, t1, p)
+        assert rc == capi.OK and flags == 0
+        sub = slice(0, None, 3)
+        ref = oracle.motion_compensate_frame(cloud[sub], stamps[sub], T_start, T_end, t0, t2, t1)
+        err = float(np.abs(out[sub, :3] - ref[:, :3]).max())
+        print(f"f64 layout: max|dxyz| = {err:.3e} m")
+        assert err < 1e-6
+        assert np.array_equal(out[:, 3], np.ones(n))
+        # a stamp outside [t_start, t_end] is where the reference asserts; a non-homogeneous 4th column is rejected
+        bad = stamps.copy()
+        bad[12345] = t2 + 1e-3
+        _, flags, rc = h.deskew_cloud_f64(cloud, bad, t0, t2, t1, p)
+        assert rc == capi.ERR_TIME_OUT_OF_RANGE and flags & 1
+        cloud_w = cloud.copy()
+        cloud_w[7, 3] = 2.0
+        _, flags, rc = h.deskew_cloud_f64(cloud_w, stamps, t0, t2, t1, p)
+        assert rc == capi.ERR_BAD_SIZE and flags & 2
+        _, _, rc = h.deskew_cloud_f64(cloud, stamps, t0, t2, t2 + 1.0, p)
+        assert rc == capi.ERR_TIME_OUT_OF_RANGE
+        # empty cloud
+        out0, flags, rc = h.deskew_cloud_f64(np.zeros((0, 4)), np.zeros(0), t0, t2, t1, p)
+        assert rc == capi.OK and out0.shape == (0, 4)

@@ -8,6 +8,7 @@
 
 Writes gpurun_out/configs.json.  The oracle is used here only as the checker / CPU timing of config 1.
 """
+import ctypes as C
 import json
 import os
 import statistics
@@ -64,6 +65,28 @@ def main():
                                 "kernel_us_l2_flushed_median": cold_med * 1e3, "mpoints_per_s_flushed": len(pts) / (cold_med * 1e-3) / 1e6,
                                 "oracle_cpu_seconds_1_thread": cpu_s, "oracle_mpoints_per_s_1_thread": len(pts) / cpu_s / 1e6,
                                 "max_abs_err_m": err}
+
+    # the reference-layout entry point (what kmc::MotionCompensateFrame(Frame, t) calls): column-major double cloud +
+    # per-point stamps from pageable host memory, result back into pageable host memory
+    cloud = np.concatenate([pts[:, :3].astype(np.float64), np.ones((len(pts), 1))], axis=1)
+    stamps = ob.pseudo_time_stamps(cloud, t0, t2)
+    with capi.Handle(0, 1024) as h:
+        for _ in range(3):
+            res64, flags, rc = h.deskew_cloud_f64(cloud, stamps, t0, t2, t1, p)
+        cm = np.ascontiguousarray(cloud.T)
+        out64 = np.empty_like(cm)
+        dp = C.POINTER(C.c_double)
+        t = []
+        for _ in range(30):
+            a = time.perf_counter()
+            capi.lib().kmc_b200_deskew_cloud_f64_host(h.raw, cm.ctypes.data_as(dp), stamps.ctypes.data_as(dp), out64.ctypes.data_as(dp),
+                                                      len(pts), t0, t2, t1, C.byref(p), None)
+            t.append(time.perf_counter() - a)
+        ref64 = ob.motion_compensate_frame(cloud[::5], stamps[::5], T_start, T_end, t0, t2, t1)
+        out["config1_reference_layout_f64_host_call"] = {
+            "us_median": statistics.median(t) * 1e6, "mpoints_per_s": len(pts) / statistics.median(t) / 1e6,
+            "max_abs_err_m": float(np.abs(res64[::5, :3] - ref64[:, :3]).max()),
+            "speedup_vs_oracle_1_thread": cpu_s / statistics.median(t)}
 
     # ---- config 2 ---------------------------------------------------------------------------------------------------
     n = 130_000

@@ -235,6 +235,10 @@ KMC_B200_API int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double
 /* GetPseudoTimeStamps on host columns x, y (length n each): H2D + kernel + D2H. */
 KMC_B200_API int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n_points,
                                                      double scan_start, double scan_end, double* stamps_out);
+/* Projection of a host scan (n x 4 float32 xyzi) onto one camera: H2D + kernel + D2H, chunked like the deskew calls.
+ * uvzc_out receives n x 4 float32 (u, v, z_rect, colour | -1), see kmc_b200_project_frame_device. */
+KMC_B200_API int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* xyzi_in, float* uvzc_out, int64_t n_points,
+                                             const kmc_b200_camera_params* camera);
 /* KITTI .bin in, deskewed .bin out (KittiPclLoader::LoadPointcloud + MotionCompensateFrame + WritePointcloud,
  * data_io.cpp:101-138, 287-313) without the float->double->float round trip.  n_points_out may be NULL. */
 KMC_B200_API int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out,

@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 DROPIN_HEADERS = ["data_types.hpp", "eigen_shim.hpp", "lie_algebra.hpp", "trajectory_interpolation.hpp", "timestamp_mocking.hpp",
-                  "motion_compensation.hpp", "data_io.hpp", "handlers.hpp", "utils.hpp", "data_handle.hpp"]
+                  "motion_compensation.hpp", "camera_model.hpp", "data_io.hpp", "handlers.hpp", "utils.hpp", "data_handle.hpp"]
 
 
 def _cxx() -> str:

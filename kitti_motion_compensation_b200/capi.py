@@ -107,6 +107,7 @@ SIGNATURES = {
     "kmc_b200_deskew_cloud_f64_host": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int64, C.c_double, C.c_double, C.c_double,
                                                  C.POINTER(FrameParams), C.POINTER(C.c_int)]),
     "kmc_b200_pseudo_time_stamps_xy_host": (C.c_int, [_vp, _dp, _dp, C.c_int64, C.c_double, C.c_double, _dp]),
+    "kmc_b200_project_frame_host": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(CameraParams)]),
     "kmc_b200_deskew_bin_file": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.POINTER(FrameParams), C.POINTER(C.c_int64)]),
 }
 
@@ -357,6 +358,13 @@ class Handle:
         ys = np.ascontiguousarray(y, dtype=np.float64)
         out = np.empty_like(xs)
         check(lib().kmc_b200_pseudo_time_stamps_xy_host(self._h, _ptr(xs), _ptr(ys), xs.size, start, end, _ptr(out)))
+        return out
+
+    def project_frame(self, xyzi: np.ndarray, camera: CameraParams) -> np.ndarray:
+        """(n,4) float32 xyzi -> (n,4) float32 (u, v, z_rect, colour | -1)."""
+        pts = np.ascontiguousarray(xyzi, dtype=np.float32).reshape(-1, 4)
+        out = np.empty_like(pts)
+        check(lib().kmc_b200_project_frame_host(self._h, pts.ctypes.data, out.ctypes.data, pts.shape[0], C.byref(camera)))
         return out
 
     def deskew_bin_file(self, path_in: str, path_out: str, params: FrameParams) -> int:

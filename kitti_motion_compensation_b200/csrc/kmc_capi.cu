@@ -704,6 +704,24 @@ int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, con
   return KMC_B200_OK;
 }
 
+int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* in, float* uvzc_out, int64_t n, const kmc_b200_camera_params* camera) {
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "project_frame_host: null handle");
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "project_frame_host: negative n_points");
+  if (!camera) return Fail(KMC_B200_ERR_NULL_POINTER, "project_frame_host: null camera params");
+  if (n == 0) return KMC_B200_OK;
+  if (!in || !uvzc_out) return Fail(KMC_B200_ERR_NULL_POINTER, "project_frame_host: null point buffer");
+  if (in == uvzc_out) return Fail(KMC_B200_ERR_BAD_SIZE, "project_frame_host: the pixel buffer must not alias the cloud");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  kmc_b200_camera_params const K = *camera;
+  return StreamThroughDevice(h, in, uvzc_out, n, [&](int slot, int64_t, int64_t count) -> int {
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchProject(h->d_in[slot], nullptr, h->d_out[slot], count, nullptr, K, KMC_B200_TIME_FROM_AZIMUTH, true,
+                                              h->sm_count, h->stream[slot]));
+    return KMC_B200_OK;
+  });
+}
+
 int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out, const kmc_b200_frame_params* params,
                              int64_t* n_points_out) {
   if (!h || !path_in || !path_out || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_file: null argument");

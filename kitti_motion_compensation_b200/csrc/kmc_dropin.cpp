@@ -21,6 +21,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "kitti_motion_compensation/camera_model.hpp"
 #include "kitti_motion_compensation/data_handle.hpp"
 #include "kitti_motion_compensation/data_io.hpp"
 #include "kitti_motion_compensation/handlers.hpp"
@@ -448,4 +449,110 @@ KMC_EXPORT void MotionCompensateRun(Path const run_folder) {
   }
 }
 
+// ---- calibration files + projection (camera_model.cpp, data_io.cpp:168-210,321-406) -----------------------------------------
+namespace {
+std::vector<double> NumbersAfterLabel(std::string const& line, size_t expected, char const* what) {
+  std::vector<std::string> const tokens{TokenizeString(line)};  // "R_rect_00: 9.99e-01 ..."
+  if (tokens.size() < expected + 1) throw std::runtime_error(std::string("Calibration line is too short for ") + what + ": " + line);
+  std::vector<double> values;
+  for (size_t i{1}; i <= expected; ++i) values.push_back(std::stod(tokens[i]));
+  return values;
+}
+template <class M>
+void FillRowMajor(M& m, std::vector<double> const& v) {
+  for (Index r = 0; r < m.rows(); ++r)
+    for (Index c = 0; c < m.cols(); ++c) m(r, c) = v[static_cast<size_t>(r * m.cols() + c)];
+}
+}  // namespace
+
+KMC_EXPORT Eigen::Affine3d LoadLidarExtrinsics(kmc::Path const data_folder, bool const to_cam) {
+  Path const file{data_folder / Path(to_cam ? "calib_velo_to_cam.txt" : "calib_imu_to_velo.txt")};
+  std::ifstream in(file);
+  if (!in.is_open()) {
+    std::cout << "Failed to open camera calibration file: " << file << '\n';
+    std::exit(0);  // the reference's convention (data_io.cpp:178-181)
+  }
+  std::string line;
+  std::getline(in, line);  // calib_time
+  std::getline(in, line);
+  Eigen::Matrix3d R;
+  FillRowMajor(R, NumbersAfterLabel(line, 9, "R"));
+  std::getline(in, line);
+  std::vector<double> const t{NumbersAfterLabel(line, 3, "T")};
+  Eigen::Affine3d T{Eigen::Affine3d::Identity()};
+  T.linear() = R;
+  T.translation() = Eigen::Vector3d{t[0], t[1], t[2]};
+  return T;
+}
+
 }  // namespace kmc
+
+namespace kmc::viz {
+
+KMC_EXPORT CameraCalibration CalibrationLinesToCalibration(std::vector<std::string> const lines) {
+  if (lines.size() < 8) throw std::runtime_error("A camera calibration block has eight lines (S K D R T S_rect R_rect P_rect)");
+  CameraCalibration c;
+  std::vector<double> v{NumbersAfterLabel(lines[0], 2, "S")};
+  c.S = Eigen::Vector2d{v[0], v[1]};
+  FillRowMajor(c.K, NumbersAfterLabel(lines[1], 9, "K"));
+  FillRowMajor(c.D, NumbersAfterLabel(lines[2], 5, "D"));
+  FillRowMajor(c.R, NumbersAfterLabel(lines[3], 9, "R"));
+  v = NumbersAfterLabel(lines[4], 3, "T");
+  c.T = Eigen::Vector3d{v[0], v[1], v[2]};
+  v = NumbersAfterLabel(lines[5], 2, "S_rect");
+  c.S_rect = Eigen::Vector2d{v[0], v[1]};
+  FillRowMajor(c.R_rect, NumbersAfterLabel(lines[6], 9, "R_rect"));
+  FillRowMajor(c.P_rect, NumbersAfterLabel(lines[7], 12, "P_rect"));
+  return c;
+}
+
+KMC_EXPORT CameraCalibrations LoadCameraCalibrations(kmc::Path const data_folder) {
+  Path const file{data_folder / Path("calib_cam_to_cam.txt")};
+  std::ifstream in(file);
+  if (!in.is_open()) {
+    std::cout << "Failed to open camera calibration file: " << file << '\n';
+    std::exit(0);  // data_io.cpp:379-382
+  }
+  std::string line;
+  std::getline(in, line);  // calib_time
+  std::getline(in, line);  // corner_dist
+  std::vector<CameraCalibration> cameras;
+  for (int cam = 0; cam < 4; ++cam) {
+    std::vector<std::string> block;
+    for (int i = 0; i < 8; ++i) {
+      std::getline(in, line);
+      block.push_back(line);
+    }
+    cameras.push_back(CalibrationLinesToCalibration(block));
+  }
+  return CameraCalibrations{cameras[0], cameras[1], cameras[2], cameras[3]};
+}
+
+KMC_EXPORT std::vector<ProjectedPoint> ProjectPointcloudOnCamera(Pointcloud const& cloud, CameraCalibration const& camera,
+                                                                 Eigen::Matrix3d const& r_rect_00, Eigen::Affine3d const& tf_c00_lo,
+                                                                 double const max_range) {
+  double p_rect[12], r_rect[9], tf[16];
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 3; ++r) p_rect[c * 3 + r] = camera.P_rect(r, c);
+  ToBuffer(r_rect_00, r_rect);
+  ToBuffer(tf_c00_lo, tf);
+  kmc_b200_camera_params params{};
+  ThrowUnlessOk(kmc_b200_camera_params_from_calibration(p_rect, r_rect, tf, max_range, &params), "kmc_b200_camera_params_from_calibration");
+  Index const n{cloud.rows()};
+  std::vector<ProjectedPoint> result(static_cast<size_t>(n));
+  if (n == 0) return result;
+  std::vector<float> xyzi(static_cast<size_t>(4 * n));
+  const double* c = cloud.data();
+  for (Index i = 0; i < n; ++i) {
+    xyzi[static_cast<size_t>(4 * i)] = static_cast<float>(c[i]);
+    xyzi[static_cast<size_t>(4 * i + 1)] = static_cast<float>(c[n + i]);
+    xyzi[static_cast<size_t>(4 * i + 2)] = static_cast<float>(c[2 * n + i]);
+    xyzi[static_cast<size_t>(4 * i + 3)] = 0.0f;
+  }
+  static_assert(sizeof(ProjectedPoint) == 4 * sizeof(float), "ProjectedPoint mirrors the kernel's float4 record");
+  ThrowUnlessOk(kmc_b200_project_frame_host(DefaultHandle(), xyzi.data(), reinterpret_cast<float*>(result.data()), n, &params),
+                "kmc_b200_project_frame_host");
+  return result;
+}
+
+}  // namespace kmc::viz

@@ -9,6 +9,7 @@
 #include <memory>
 #include <random>
 
+#include "kitti_motion_compensation/camera_model.hpp"
 #include "kitti_motion_compensation/data_handle.hpp"
 #include "kitti_motion_compensation/data_io.hpp"
 #include "kitti_motion_compensation/data_types.hpp"
@@ -259,6 +260,45 @@ TEST(DataHandleTest, FloatPathMatchesFrameApi) {
   ASSERT_FLOAT_EQ(out[3], 0.7);
   ASSERT_FLOAT_EQ(out[11], 0.9);
   ASSERT_THROW(kmc::b200::FrameParamsFromPoses(Ts.data(), Te.data(), 0.1, 0.2, 0.5), std::runtime_error);
+}
+
+// ---- camera_model.cpp:5-95 without the drawing: the draw list of the real scan on camera 02 ------------------------------
+TEST(CameraModelTest, ProjectPointcloudOnCamera) {
+  KittiPclLoader loader;
+  auto const [cloud, intensities] = loader.LoadPointcloud(g_real_scan);
+  viz::CameraCalibration cam;
+  cam.P_rect << 7.215377e+02, 0.0, 6.095593e+02, 4.485728e+01, 0.0, 7.215377e+02, 1.728540e+02, 2.163791e-01, 0.0, 0.0, 1.0, 2.745884e-03;
+  Eigen::Matrix3d r_rect;
+  r_rect << 9.999239e-01, 9.837760e-03, -7.445048e-03, -9.869795e-03, 9.999421e-01, -4.278459e-03, 7.402527e-03, 4.351614e-03, 9.999631e-01;
+  Eigen::Matrix3d R;
+  R << 7.533745e-03, -9.999714e-01, -6.166020e-04, 1.480249e-02, 7.280733e-04, -9.998902e-01, 9.998621e-01, 7.523790e-03, 1.480755e-02;
+  Eigen::Affine3d tf{Eigen::Affine3d::Identity()};
+  tf.linear() = R;
+  tf.translation() = Eigen::Vector3d{-4.069766e-03, -7.631618e-02, -2.717806e-01};
+
+  auto const draw{viz::ProjectPointcloudOnCamera(cloud, cam, r_rect, tf, 15.0)};
+  ASSERT_EQ(static_cast<Index>(draw.size()), cloud.rows());
+  int kept = 0, checked = 0;
+  for (Index i = 0; i < cloud.rows(); i += 13) {
+    Eigen::Vector3d const p{cloud.row(i)(0), cloud.row(i)(1), cloud.row(i)(2)};
+    Eigen::Vector3d const rect{r_rect * (tf * p)};  // R_rect_00 * (R|T) * X   (camera_model.cpp:75-81)
+    bool const keep = !((rect(2) < 0.01) || (rect(2) > 15.0) || (rect(1) > 1.25));  // :21-23
+    bool const near_edge = std::fabs(rect(2) - 0.01) < 1e-4 || std::fabs(rect(2) - 15.0) < 1e-4 || std::fabs(rect(1) - 1.25) < 1e-4;
+    if (!near_edge) ASSERT_TRUE(draw[static_cast<size_t>(i)].kept() == keep);
+    if (!keep || rect(2) < 0.5) continue;
+    ++kept;
+    double const pu = cam.P_rect(0, 0) * rect(0) + cam.P_rect(0, 1) * rect(1) + cam.P_rect(0, 2) * rect(2) + cam.P_rect(0, 3);
+    double const pv = cam.P_rect(1, 0) * rect(0) + cam.P_rect(1, 1) * rect(1) + cam.P_rect(1, 2) * rect(2) + cam.P_rect(1, 3);
+    double const pw = cam.P_rect(2, 0) * rect(0) + cam.P_rect(2, 1) * rect(1) + cam.P_rect(2, 2) * rect(2) + cam.P_rect(2, 3);
+    if (std::fabs(pu / pw) > 2000.0) continue;  // far off the 1242 x 375 image
+    ++checked;
+    ASSERT_NEAR(draw[static_cast<size_t>(i)].u, pu / pw, 2e-2);
+    ASSERT_NEAR(draw[static_cast<size_t>(i)].v, pv / pw, 2e-2);
+    ASSERT_NEAR(draw[static_cast<size_t>(i)].depth, rect(2), 1e-5);
+    ASSERT_NEAR(draw[static_cast<size_t>(i)].colour, 255.0 * rect(2) / 14.99, 1e-3);
+  }
+  std::printf("    %d sampled points kept by the reference's filters, %d compared on the image\n", kept, checked);
+  ASSERT_TRUE(checked > 100);
 }
 
 int main(int argc, char** argv) {

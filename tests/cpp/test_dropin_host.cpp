@@ -1,5 +1,9 @@
 // Host-only part of the C++ mirror tests: the reference's test/test_lie_algebra.cpp and the artificial-pose half of
 // test/test_trajectory_interpolation.cpp, re-expressed against this repository's drop-in headers.  No GPU needed.
+#include <filesystem>
+#include <fstream>
+
+#include "kitti_motion_compensation/camera_model.hpp"
 #include "kitti_motion_compensation/data_io.hpp"
 #include "kitti_motion_compensation/lie_algebra.hpp"
 #include "kitti_motion_compensation/trajectory_interpolation.hpp"
@@ -118,6 +122,55 @@ TEST(UtilsTest, StringHelpers) {
   auto const tokens{TokenizeString("2011-09-26 13:04:32.283701593")};
   ASSERT_EQ(tokens.size(), size_t{2});
   ASSERT_NEAR(MmHhSsToSeconds(tokens[1]), 47072.283701593, 1e-9);  // test/test_data_io.cpp:49
+}
+
+// ---- calibration parsers (data_io.cpp:168-210, 321-406) on files with the reference's calibration values -----------------
+static std::filesystem::path WriteCalibrationFolder() {
+  namespace fs = std::filesystem;
+  fs::path const dir{fs::temp_directory_path() / "kmc_b200_test_calib"};
+  fs::create_directories(dir);
+  std::ofstream velo(dir / "calib_velo_to_cam.txt");
+  velo << "calib_time: 15-Mar-2012 11:37:16\n"
+       << "R: 7.533745e-03 -9.999714e-01 -6.166020e-04 1.480249e-02 7.280733e-04 -9.998902e-01 9.998621e-01 7.523790e-03 1.480755e-02\n"
+       << "T: -4.069766e-03 -7.631618e-02 -2.717806e-01\n"
+       << "delta_f: 0.000000e+00 0.000000e+00\n";
+  std::ofstream cam(dir / "calib_cam_to_cam.txt");
+  cam << "calib_time: 09-Jan-2012 13:57:47\ncorner_dist: 9.950000e-02\n";
+  const char* p_rect[4] = {"0.000000e+00 0.000000e+00 7.215377e+02 1.728540e+02 0.000000e+00", "-3.875744e+02 0.000000e+00 7.215377e+02 1.728540e+02 0.000000e+00",
+                           "4.485728e+01 0.000000e+00 7.215377e+02 1.728540e+02 2.163791e-01", "-3.395242e+02 0.000000e+00 7.215377e+02 1.728540e+02 2.199936e+00"};
+  const char* p_tail[4] = {"0.000000e+00", "0.000000e+00", "2.745884e-03", "2.729905e-03"};
+  for (int c = 0; c < 4; ++c) {
+    cam << "S_0" << c << ": 1.392000e+03 5.120000e+02\n"
+        << "K_0" << c << ": 9.842439e+02 0.000000e+00 6.900000e+02 0.000000e+00 9.808141e+02 2.331966e+02 0.000000e+00 0.000000e+00 1.000000e+00\n"
+        << "D_0" << c << ": -3.728755e-01 2.037299e-01 2.219027e-03 1.383707e-03 -7.233722e-02\n"
+        << "R_0" << c << ": 1.000000e+00 0.000000e+00 0.000000e+00 0.000000e+00 1.000000e+00 0.000000e+00 0.000000e+00 0.000000e+00 1.000000e+00\n"
+        << "T_0" << c << ": " << -0.5 * c << " 0.000000e+00 0.000000e+00\n"
+        << "S_rect_0" << c << ": 1.242000e+03 3.750000e+02\n"
+        << "R_rect_0" << c << ": 9.999239e-01 9.837760e-03 -7.445048e-03 -9.869795e-03 9.999421e-01 -4.278459e-03 7.402527e-03 4.351614e-03 9.999631e-01\n"
+        << "P_rect_0" << c << ": 7.215377e+02 0.000000e+00 6.095593e+02 " << p_rect[c] << " 0.000000e+00 0.000000e+00 1.000000e+00 " << p_tail[c] << "\n";
+  }
+  return dir;
+}
+
+TEST(CalibrationIoTest, LoadLidarExtrinsicsAndCameraCalibrations) {
+  auto const dir{WriteCalibrationFolder()};
+  Eigen::Affine3d const tf{LoadLidarExtrinsics(dir, true)};
+  ASSERT_FLOAT_EQ(tf.linear()(0, 1), -9.999714e-01);
+  ASSERT_FLOAT_EQ(tf.linear()(2, 0), 9.998621e-01);
+  ASSERT_FLOAT_EQ(tf.translation()(2), -2.717806e-01);
+  viz::CameraCalibrations const cams{viz::LoadCameraCalibrations(dir)};
+  ASSERT_FLOAT_EQ(cams.camera_00.S_rect(0), 1242.0);
+  ASSERT_FLOAT_EQ(cams.camera_00.R_rect(0, 1), 9.837760e-03);
+  ASSERT_FLOAT_EQ(cams.camera_00.R_rect(1, 0), -9.869795e-03);
+  ASSERT_FLOAT_EQ(cams.camera_02.P_rect(0, 0), 7.215377e+02);
+  ASSERT_FLOAT_EQ(cams.camera_02.P_rect(0, 2), 6.095593e+02);
+  ASSERT_FLOAT_EQ(cams.camera_02.P_rect(0, 3), 4.485728e+01);
+  ASSERT_FLOAT_EQ(cams.camera_02.P_rect(1, 3), 2.163791e-01);
+  ASSERT_FLOAT_EQ(cams.camera_02.P_rect(2, 3), 2.745884e-03);
+  ASSERT_FLOAT_EQ(cams.camera_03.P_rect(0, 3), -3.395242e+02);
+  ASSERT_FLOAT_EQ(cams.camera_01.T(0), -0.5);
+  ASSERT_FLOAT_EQ(cams.camera_00.D(4), -7.233722e-02);
+  std::filesystem::remove_all(dir);
 }
 
 int main(int argc, char** argv) {

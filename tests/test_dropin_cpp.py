@@ -28,7 +28,9 @@ def test_dropin_library_exports_the_reference_symbols():
                 "kmc::trajectory_interpolation::InterpolateTrajectory(kmc::Oxts const&, kmc::Oxts const&, double)",
                 "kmc::lie::Hat(", "kmc::lie::Vee(", "kmc::lie::Exp(", "kmc::lie::Log(", "kmc::lie::LeftJacobian(",
                 "kmc::lie::InverseLeftJacobian(", "kmc::OxtsToPose(kmc::Oxts const&, double)", "kmc::MakeFrame(",
-                "kmc::KittiPclLoader::LoadPointcloud(", "kmc::WritePointcloud(", "kmc::MotionCompensateRun("]:
+                "kmc::KittiPclLoader::LoadPointcloud(", "kmc::WritePointcloud(", "kmc::MotionCompensateRun(",
+                "kmc::LoadLidarExtrinsics(", "kmc::viz::LoadCameraCalibrations(", "kmc::viz::CalibrationLinesToCalibration(",
+                "kmc::viz::ProjectPointcloudOnCamera("]:
         assert sym in out, sym
 
 

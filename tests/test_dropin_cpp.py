@@ -63,3 +63,15 @@ def test_motion_compensate_frame_has_no_cpu_fallback():
     r = run_binary(build.build_cpp_test("test_dropin_gpu"), "DataHandleTest", REAL_SCAN)
     assert r.returncode != 0
     assert "no usable CUDA device" in r.stderr or "CUDA" in r.stderr
+
+
+def test_eigen_shim_semantics():
+    """The fallback Eigen subset (column-major storage, comma initialiser, row proxies, Affine-mode inverse / rotation())."""
+    from kitti_motion_compensation_b200 import build
+    tests = os.path.join(ROOT, "tests", "cpp")
+    out = os.path.join(tests, "_build", "test_eigen_shim")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run([build._cxx(), "-std=c++17", "-O1", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-I", tests, "-o", out, os.path.join(tests, "test_eigen_shim.cpp")], check=True)
+    r = run_binary(out)
+    assert r.returncode == 0 and " 0 failed" in r.stdout

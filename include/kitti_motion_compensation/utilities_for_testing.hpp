@@ -1,5 +1,7 @@
-// utilities_for_testing.hpp — comparison helpers with the semantics of the reference's
-// include/kitti_motion_compensation/utilities_for_testing.hpp:4-11 (float-cast trace / off-trace sum of A * B^-1).
+// utilities_for_testing.hpp — pose comparison helper with the semantics of the reference's test utility
+// (reference include/kitti_motion_compensation/utilities_for_testing.hpp:4-11): two transforms count as equal when
+// A * B^-1 has, after rounding to float, a trace of exactly 4 and off-diagonal entries summing to exactly 0
+// (tolerance 1e-10, i.e. effectively float equality).
 #pragma once
 
 #include <cmath>
@@ -8,13 +10,23 @@
 
 namespace kmc::utilities_for_testing {
 
-inline bool FloatEqual(float const a, float const b, float const epsilon = 1e-10) { return std::fabs(a - b) <= epsilon; }
+inline bool FloatEqual(float const a, float const b, float const epsilon = 1e-10) {
+  float const gap{std::fabs(a - b)};
+  return gap <= epsilon;
+}
 
-// true when tf1 * tf2^-1 is the identity to float precision
 inline bool TransformationMatricesAreTheSame(Affine3d const& tf1, Affine3d const& tf2) {
-  auto const product{tf1 * tf2.inverse()};
-  auto const m{product.matrix()};
-  return FloatEqual(static_cast<float>(m.trace()), 4.0f) and FloatEqual(static_cast<float>(m.sum() - m.trace()), 0.0f);
+  Affine3d const should_be_identity{tf1 * tf2.inverse()};
+  double diagonal{1.0};  // the homogeneous corner
+  double everything{1.0};
+  for (int r = 0; r < 3; ++r) {
+    diagonal += should_be_identity.linear()(r, r);
+    everything += should_be_identity.translation()(r);
+    for (int c = 0; c < 3; ++c) everything += should_be_identity.linear()(r, c);
+  }
+  bool const trace_is_four{FloatEqual(static_cast<float>(diagonal), 4.0f)};
+  bool const rest_is_zero{FloatEqual(static_cast<float>(everything - diagonal), 0.0f)};
+  return trace_is_four && rest_is_zero;
 }
 
 }  // namespace kmc::utilities_for_testing

@@ -16,7 +16,33 @@
 #include "kmc_host_math.hpp"
 #include "kmc_kernels.cuh"
 
+// NVTX ranges around the host entry points (visible in Nsight Systems / Compute timelines); header-only, no cost when
+// no tool is attached.
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define KMC_HAVE_NVTX 1
+#else
+#define KMC_HAVE_NVTX 0
+#endif
+
 namespace {
+
+struct TraceRange {
+  explicit TraceRange(const char* name) {
+#if KMC_HAVE_NVTX
+    nvtxRangePushA(name);
+#else
+    (void)name;
+#endif
+  }
+  ~TraceRange() {
+#if KMC_HAVE_NVTX
+    nvtxRangePop();
+#endif
+  }
+  TraceRange(TraceRange const&) = delete;
+  TraceRange& operator=(TraceRange const&) = delete;
+};
 
 thread_local std::string t_last_error;
 
@@ -567,6 +593,7 @@ int64_t kmc_b200_handle_capacity(const kmc_b200_handle* h) { return h ? h->capac
 // ---- host entry points -------------------------------------------------------------------------------------------------
 int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, int64_t n, const kmc_b200_frame_params* params,
                                int mode) {
+  TraceRange const trace("kmc_b200_deskew_frame_host");
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_host: null handle");
   if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_frame_host: negative n_points");
   if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_frame_host: unknown time mode");
@@ -586,6 +613,7 @@ int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, 
 
 int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* in, float* out, const int64_t* offsets,
                                const kmc_b200_frame_params* params, int32_t n_frames, int mode) {
+  TraceRange const trace("kmc_b200_deskew_batch_host");
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_host: null handle");
   if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_host: negative n_frames");
   if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_batch_host: unknown time mode");
@@ -613,6 +641,7 @@ int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* in, float* out, 
 
 int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_handles, const float* in, float* out,
                                     const int64_t* offsets, const kmc_b200_frame_params* params, int32_t n_frames, int mode) {
+  TraceRange const trace("kmc_b200_deskew_batch_multi_gpu");
   if (!handles || n_handles <= 0) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_multi_gpu: no handles");
   if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_multi_gpu: negative n_frames");
   if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_batch_multi_gpu: unknown time mode");
@@ -648,6 +677,7 @@ int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_h
 
 int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, const double* stamps, double* out, int64_t n, double t_start,
                                    double t_end, double t_req, const kmc_b200_frame_params* params, int* flags_out) {
+  TraceRange const trace("kmc_b200_deskew_cloud_f64_host");
   if (flags_out) *flags_out = 0;
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null handle");
   if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_cloud_f64_host: negative n_points");
@@ -684,6 +714,7 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
 
 int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n, double start, double end,
                                         double* stamps) {
+  TraceRange const trace("kmc_b200_pseudo_time_stamps_xy_host");
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_xy_host: null handle");
   if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_xy_host: negative n_points");
   if (n == 0) return KMC_B200_OK;
@@ -705,6 +736,7 @@ int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, con
 }
 
 int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* in, float* uvzc_out, int64_t n, const kmc_b200_camera_params* camera) {
+  TraceRange const trace("kmc_b200_project_frame_host");
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "project_frame_host: null handle");
   if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "project_frame_host: negative n_points");
   if (!camera) return Fail(KMC_B200_ERR_NULL_POINTER, "project_frame_host: null camera params");
@@ -724,6 +756,7 @@ int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* in, float* uvzc
 
 int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out, const kmc_b200_frame_params* params,
                              int64_t* n_points_out) {
+  TraceRange const trace("kmc_b200_deskew_bin_file");
   if (!h || !path_in || !path_out || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_file: null argument");
   FILE* f = std::fopen(path_in, "rb");
   if (!f) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path_in);

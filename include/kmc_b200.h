@@ -193,6 +193,12 @@ KMC_B200_API int kmc_b200_project_frame_device(const float* xyzi_in, float* uvzc
 KMC_B200_API int kmc_b200_deskew_project_frame_device(const float* xyzi_in, float* xyzi_out, float* uvzc_out, int64_t n_points,
                                                       const kmc_b200_frame_params* params_host,
                                                       const kmc_b200_camera_params* camera_host, int time_mode, void* stream);
+/* All four cameras of the KITTI rig in one pass (camera_model.cpp:85-92 projects the same cloud four times): the cloud is
+ * read once and uvzc_out[c] receives camera c's records.  params_host may be NULL (projection of the input cloud as it
+ * is); with params the points are deskewed first and, if xyzi_out is not NULL, the deskewed cloud is written too. */
+KMC_B200_API int kmc_b200_deskew_project_frame4_device(const float* xyzi_in, float* xyzi_out, float* const uvzc_out[4],
+                                                       int64_t n_points, const kmc_b200_frame_params* params_host,
+                                                       const kmc_b200_camera_params cameras_host[4], int time_mode, void* stream);
 /* Seeded synthetic HDL-64E style scans written straight into device memory (benchmark input):
  * n_scans scans of points_per_scan points, scan k uses seed + first_scan_index + k, so a scan's content does not
  * depend on which GPU generates it.  n_rings x azimuth steps, ring-major, log-uniform range in [2, 120) m. */

@@ -92,6 +92,8 @@ SIGNATURES = {
                                                        C.c_int, _vp]),
     "kmc_b200_deskew_cloud_f64_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, C.c_double,
                                                    C.POINTER(FrameParams), _vp, _vp]),
+    "kmc_b200_deskew_project_frame4_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.c_int64, C.POINTER(FrameParams),
+                                                        C.POINTER(CameraParams), C.c_int, _vp]),
     "kmc_b200_pseudo_time_stamps_device": (C.c_int, [_vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_pseudo_time_stamps_xy_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_synth_scans_device": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, _vp]),
@@ -259,6 +261,15 @@ def deskew_project_frame_device(in_ptr: int, out_ptr: int, uvzc_ptr: int, n_poin
                                 mode: int = TIME_FROM_AZIMUTH, stream: int = 0) -> None:
     check(lib().kmc_b200_deskew_project_frame_device(in_ptr, out_ptr, uvzc_ptr, n_points, C.byref(params), C.byref(camera), mode,
                                                      stream))
+
+
+def deskew_project_frame4_device(in_ptr: int, out_ptr: int, uvzc_ptrs, n_points: int, params, cameras, mode: int = TIME_FROM_AZIMUTH,
+                                 stream: int = 0) -> None:
+    """Four cameras in one pass.  params may be None (project the input as it is); out_ptr may be 0."""
+    planes = (_vp * 4)(*uvzc_ptrs)
+    cams = (CameraParams * 4)(*cameras)
+    check(lib().kmc_b200_deskew_project_frame4_device(in_ptr, out_ptr, planes, n_points, C.byref(params) if params is not None else None,
+                                                      cams, mode, stream))
 
 
 def pseudo_time_stamps_device(in_ptr: int, out_ptr: int, n_points: int, start: float, end: float, stream: int = 0) -> None:

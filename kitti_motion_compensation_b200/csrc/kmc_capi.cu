@@ -477,6 +477,29 @@ int kmc_b200_deskew_cloud_f64_device(const double* cloud, const double* stamps, 
   return KMC_B200_OK;
 }
 
+int kmc_b200_deskew_project_frame4_device(const float* in, float* xyzi_out, float* const uvzc_out[4], int64_t n,
+                                          const kmc_b200_frame_params* params, const kmc_b200_camera_params cameras[4], int mode,
+                                          void* stream) {
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_frame4_device: negative n_points");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_project_frame4_device: unknown time mode");
+  if (!cameras || !uvzc_out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_project_frame4_device: null camera / output table");
+  if (n == 0) return KMC_B200_OK;
+  if (!in) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_project_frame4_device: null point buffer");
+  if (!Aligned(in, 16) || (xyzi_out && !Aligned(xyzi_out, 16))) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_frame4_device: misaligned cloud");
+  for (int c = 0; c < 4; ++c) {
+    if (!uvzc_out[c]) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_project_frame4_device: null pixel buffer");
+    if (!Aligned(uvzc_out[c], 16)) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_frame4_device: misaligned pixel buffer");
+    if (uvzc_out[c] == in || uvzc_out[c] == xyzi_out) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_frame4_device: a pixel buffer aliases a cloud");
+    for (int d = 0; d < c; ++d)
+      if (uvzc_out[c] == uvzc_out[d]) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_frame4_device: pixel buffers must be distinct");
+  }
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchProject4(in, xyzi_out, uvzc_out, n, params, cameras, mode, sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
 int kmc_b200_pseudo_time_stamps_device(const float* in, double* stamps, int64_t n, double start, double end, void* stream) {
   if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_device: negative n_points");
   if (n == 0) return KMC_B200_OK;

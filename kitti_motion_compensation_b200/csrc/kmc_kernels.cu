@@ -258,6 +258,31 @@ __global__ void __launch_bounds__(kBlockThreads)
   }
 }
 
+// All four rectified cameras in one pass (camera_model.cpp:85-92 projects the same cloud four times): the cloud is read
+// once, four pixel records are written.  16 (+16 with the deskewed cloud) + 4 x 16 B/point instead of 4 x 32.
+struct Cameras4 {
+  kmc_b200_camera_params cam[4];
+};
+struct PixelPlanes4 {
+  float4* plane[4];
+};
+
+template <bool DESKEW, bool WRITE_CLOUD, int MODE>
+__global__ void __launch_bounds__(kBlockThreads)
+    ProjectFrame4Kernel(const float4* __restrict__ in, float4* __restrict__ cloud_out, PixelPlanes4 const pix_out, int64_t n,
+                        const __grid_constant__ kmc_b200_frame_params P, const __grid_constant__ Cameras4 K) {
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; i < n; i += stride) {
+    float4 p = LoadPoint<0>(in + i);
+    if constexpr (DESKEW) {
+      p = DeskewPoint<MODE>(p, P);
+      if constexpr (WRITE_CLOUD) StorePoint<0>(cloud_out + i, p);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) StorePoint<0>(pix_out.plane[c] + i, ProjectPoint(p, K.cam[c]));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // The reference's own memory layout (motion_compensation.cpp:16-28): cloud and result are COLUMN-major N x 4 doubles
 // (Eigen::MatrixX4d), per-point stamps a separate double vector.  Used by the C++ mirror of MotionCompensateFrame so that
@@ -571,6 +596,35 @@ cudaError_t LaunchProject(const float* in, float* cloud_out, float* pix_out, int
   }
   return az ? LaunchProjectT<true, false, KMC_B200_TIME_FROM_AZIMUTH>(in, nullptr, pix_out, n, *params, camera, vec2, sm_count, stream)
             : LaunchProjectT<true, false, KMC_B200_TIME_FROM_W>(in, nullptr, pix_out, n, *params, camera, vec2, sm_count, stream);
+}
+
+cudaError_t LaunchProject4(const float* in, float* cloud_out, float* const pix_out[4], int64_t n, const kmc_b200_frame_params* params,
+                           const kmc_b200_camera_params cameras[4], int mode, int sm_count, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  Cameras4 K;
+  PixelPlanes4 planes;
+  for (int c = 0; c < 4; ++c) {
+    K.cam[c] = cameras[c];
+    planes.plane[c] = reinterpret_cast<float4*>(pix_out[c]);
+  }
+  int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
+  int64_t const cap = static_cast<int64_t>(sm_count) * 5;
+  if (grid > cap) grid = cap;
+  auto const* in4 = reinterpret_cast<const float4*>(in);
+  auto* cloud4 = reinterpret_cast<float4*>(cloud_out);
+  unsigned const g = static_cast<unsigned>(grid);
+  kmc_b200_frame_params const none{};
+  if (!params) {
+    ProjectFrame4Kernel<false, false, 0><<<g, kBlockThreads, 0, stream>>>(in4, nullptr, planes, n, none, K);
+  } else if (mode == KMC_B200_TIME_FROM_AZIMUTH) {
+    if (cloud_out) ProjectFrame4Kernel<true, true, KMC_B200_TIME_FROM_AZIMUTH><<<g, kBlockThreads, 0, stream>>>(in4, cloud4, planes, n, *params, K);
+    else ProjectFrame4Kernel<true, false, KMC_B200_TIME_FROM_AZIMUTH><<<g, kBlockThreads, 0, stream>>>(in4, nullptr, planes, n, *params, K);
+  } else {
+    if (cloud_out) ProjectFrame4Kernel<true, true, KMC_B200_TIME_FROM_W><<<g, kBlockThreads, 0, stream>>>(in4, cloud4, planes, n, *params, K);
+    else ProjectFrame4Kernel<true, false, KMC_B200_TIME_FROM_W><<<g, kBlockThreads, 0, stream>>>(in4, nullptr, planes, n, *params, K);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
 }
 
 cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,

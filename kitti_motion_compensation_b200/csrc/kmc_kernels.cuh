@@ -52,6 +52,10 @@ cudaError_t LaunchProject(const float* in, float* cloud_out, float* pix_out, int
 cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,
                                    cudaStream_t stream);
 
+// The same for four cameras in one pass: pix_out[c] receives camera c's records.
+cudaError_t LaunchProject4(const float* in, float* cloud_out, float* const pix_out[4], int64_t n, const kmc_b200_frame_params* params,
+                           const kmc_b200_camera_params cameras[4], int mode, int sm_count, cudaStream_t stream);
+
 // Deskew in the reference's own layout: column-major N x 4 double cloud + per-point double stamps -> column-major double.
 cudaError_t LaunchDeskewCloudF64(const double* cloud, const double* stamps, double* out, int64_t n, double t1, double t2, double x_req,
                                  const kmc_b200_frame_params& params, int* flags_dev, int sm_count, cudaStream_t stream);

@@ -134,3 +134,39 @@ def test_fused_deskew_project_equals_two_passes(capi, oracle, cuda):
     _compare(fused_pix.cpu().numpy(), uv, valid, color, rect)
     with pytest.raises(capi.KmcError):
         capi.deskew_project_frame_device(d_in.data_ptr(), fused_cloud.data_ptr(), fused_cloud.data_ptr(), n, p, cam, 0, s)
+
+
+@pytest.mark.gpu
+def test_four_cameras_in_one_pass_equal_four_launches(capi, cuda):
+    """camera_model.cpp:85-92 projects the same cloud onto image_00..03; here one kernel reads the cloud once and writes
+    the four draw lists — bit-identical to four single-camera launches, with and without the fused deskew."""
+    torch = cuda
+    T, R_rect, P = calibration()
+    cams = [capi.camera_params_from_calibration(P[k], R_rect, T, 15.0) for k in ("00", "01", "02", "03")]
+    pts = helpers.real_scan()
+    n = len(pts)
+    s = torch.cuda.current_stream().cuda_stream
+    d_in = torch.from_numpy(pts).cuda()
+    singles = [torch.empty_like(d_in) for _ in range(4)]
+    for c in range(4):
+        capi.project_frame_device(d_in.data_ptr(), singles[c].data_ptr(), n, cams[c], s)
+    planes = [torch.empty_like(d_in) for _ in range(4)]
+    capi.deskew_project_frame4_device(d_in.data_ptr(), 0, [p.data_ptr() for p in planes], n, None, cams, 0, s)
+    torch.cuda.synchronize()
+    for c in range(4):
+        assert torch.equal(planes[c], singles[c]), f"camera {c}"
+    # fused behind the deskew, cloud written as well
+    T_start, T_end, t0, t1, t2 = helpers.config1_frame()
+    p = capi.frame_params_from_poses(T_start, T_end, t0, t2, t1)
+    desk = torch.empty_like(d_in)
+    capi.deskew_frame_device(d_in.data_ptr(), desk.data_ptr(), n, p, 0, s)
+    for c in range(4):
+        capi.project_frame_device(desk.data_ptr(), singles[c].data_ptr(), n, cams[c], s)
+    cloud = torch.empty_like(d_in)
+    capi.deskew_project_frame4_device(d_in.data_ptr(), cloud.data_ptr(), [q.data_ptr() for q in planes], n, p, cams, 0, s)
+    torch.cuda.synchronize()
+    assert torch.equal(cloud, desk)
+    for c in range(4):
+        assert torch.equal(planes[c], singles[c]), f"camera {c} (fused)"
+    with pytest.raises(capi.KmcError):  # two planes aliasing each other
+        capi.deskew_project_frame4_device(d_in.data_ptr(), 0, [planes[0].data_ptr()] * 4, n, None, cams, 0, s)

@@ -161,6 +161,23 @@ def main():
         med, best = time_launches(fn, reps=20)
         proj[name] = {"bytes_per_point": bpp, "kernel_us_median": med * 1e3, "mpoints_per_s": n / (med * 1e-3) / 1e6,
                       "gb_per_s": bpp * n / (med * 1e-3) / 1e9}
+    # all four cameras: four launches (4 x 32 B/point) vs one pass (16 + 64 B/point)
+    cams = [cam] * 4
+    planes = [torch.empty_like(d_in) for _ in range(4)]
+
+    def four_launches():
+        for c in range(4):
+            capi.project_frame_device(d_in.data_ptr(), planes[c].data_ptr(), n, cams[c], stream)
+
+    for name, bpp, fn in (
+            ("project_4_cameras_four_launches", 128, four_launches),
+            ("project_4_cameras_one_pass", 80,
+             lambda: capi.deskew_project_frame4_device(d_in.data_ptr(), 0, [q.data_ptr() for q in planes], n, None, cams, 0, stream)),
+            ("deskew_project_4_cameras_one_pass_with_cloud", 96,
+             lambda: capi.deskew_project_frame4_device(d_in.data_ptr(), d_out.data_ptr(), [q.data_ptr() for q in planes], n, p, cams, 0, stream))):
+        med, best = time_launches(fn, reps=10)
+        proj[name] = {"bytes_per_point": bpp, "kernel_us_median": med * 1e3, "mpoints_per_s": n / (med * 1e-3) / 1e6,
+                      "gb_per_s": bpp * n / (med * 1e-3) / 1e9}
     out["projection_100m_points"] = proj
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w") as f:

@@ -18,7 +18,7 @@ TUNES = st.sampled_from([None, "vec=1,unroll=1,hint=0,block=128,ctas=2,item_tile
                          "bulk=1,block=256,unroll=2,stages=4,ctas=1"])
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=40, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(sizes=SIZES, seed=st.integers(0, 2**31 - 1), tune=TUNES, mode=st.sampled_from([0, 1]), capacity=st.integers(64, 30000))
 def test_random_batches_match_closed_form(capi, cuda, monkeypatch, sizes, seed, tune, mode, capacity):
     torch = cuda
@@ -54,7 +54,9 @@ def test_random_batches_match_closed_form(capi, cuda, monkeypatch, sizes, seed, 
         if a == b:
             continue
         want = helpers.closed_form_deskew(pts[a:b], xi, float(np.float32(xr)), None if fracs is None else fracs[a:b].astype(np.float64))
-        assert np.abs(out[a:b, :3] - want).max() < TOL_M, (f, sizes)
+        # accuracy model of DESIGN.md §3: float32 output rounding + ~2.5e-7 of the displacement (the x3 twists reach 50 m)
+        disp = float(np.abs(want - pts[a:b, :3].astype(np.float64)).max())
+        assert np.abs(out[a:b, :3] - want).max() < max(TOL_M, 4e-6 + 3e-7 * disp), (f, sizes)
     assert out[:, 3].tobytes() == pts[:, 3].tobytes()
     if n:
         with capi.Handle(0, capacity) as h:

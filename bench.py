@@ -23,7 +23,6 @@ One JSON line is printed by rank 0.  Besides the contract keys it carries
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 import statistics

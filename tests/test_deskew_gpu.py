@@ -4,7 +4,6 @@ Bar (BASELINE.json north_star): max |dxyz| < 1e-5 m per coordinate vs the refere
 same float32 inputs; the w (intensity) lane is bit-exact.  There is no CPU fallback: the `cuda` fixture fails the test
 outright if no device is visible.
 """
-import ctypes as C
 import os
 
 import numpy as np

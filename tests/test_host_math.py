@@ -1,5 +1,4 @@
 """Product host code (double, once per frame) against the oracle and the reference KATs.  No GPU needed."""
-import ctypes as C
 
 import numpy as np
 import pytest

@@ -4,7 +4,7 @@
 Metric (BASELINE.json): Mpoints/s deskewed at 1/2/4/8 B200 and achieved HBM GB/s against the roofline (32 B/point).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on the host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on the host cores (oracle/_ref, else the oracle port)
 
 A "step" is one pass of the fused deskew kernel over one batch of synthetic 130 000-point HDL-64E scans that is
 already resident in HBM (BASELINE config 3: 10 000 scans = 1.3e9 points = 41.6 GB of traffic per step, far larger than
@@ -14,7 +14,7 @@ the 126 MB L2, so no L2 flush is needed between steps).  With N GPUs every rank 
 One JSON line is printed by rank 0.  Besides the contract keys it carries
   roofline      achieved algorithmic GB/s of the deskew kernel (32 B/point x points per launch / mean launch time,
                 CUDA events on the launching stream) against the measured HBM copy peak of MEASURED_PEAKS.json
-  cpu_baseline  the oracle port of the reference algorithm timed on this box's host cores on a bounded sample of the
+  cpu_baseline  the reference algorithm (oracle/_ref when built, else the oracle port) timed on this box's host cores on a bounded sample of the
                 same scans (rank 0, N=1 only) — a reported baseline, plus the max |dxyz| of the GPU result on them
   e2e           the same metric through the C ABI's host entry point (kmc_b200_deskew_batch_host): pinned host buffers,
                 H2D + kernel + D2H inside the timed region
@@ -148,49 +148,76 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_baseline_leg(pts_host: np.ndarray, xi: np.ndarray, points: int, gpu_out_host: np.ndarray | None, target_seconds: float,
                      steps: int | None = None, warmup: int = 0):
-    """Times the oracle port of the reference algorithm (per-point Log/inverse recomputation included) on the host
-    cores.  This is the one place bench.py executes oracle/.  pts_host: (frames, points, 4) float32."""
+    """Times the reference's CPU algorithm for the path (per-point Log/inverse recomputation included) on the host cores:
+    oracle/_ref (the reference's own four source files, compiled by `make -C oracle ref`) when that library is present,
+    else the oracle port.  This is the one place bench.py executes oracle/.  pts_host: (frames, points, 4) float32."""
     from oracle import binding as ob
+    from oracle import ref_binding as rb
     ob.build()
+    use_ref = rb.available()
+    engine = rb if use_ref else ob
+    if use_ref:
+        kind = "reference"
+        what = ("oracle/_ref/libkmc_ref.so = the reference's own motion_compensation / trajectory_interpolation / lie_algebra / "
+                "timestamp_mocking .cpp compiled unmodified (-O3), Eigen supplied by "
+                + ("Eigen 3" if rb.eigen_provider() == "eigen3" else "this repo's eigen_shim.hpp (no Eigen 3 in the image)"))
+    else:
+        kind = "port"
+        what = "oracle/kmc_oracle.cpp (-O3, double, reference's per-point Log/SVD/inverse kept)"
     frames_avail = pts_host.shape[0]
     cores = max(1, ob.hardware_threads())
     eye = np.eye(4)
     T_end = [ob.se3_exp(x) for x in xi[:frames_avail]]
     stamps = [[0.0, 0.1, 0.05]] * frames_avail
 
-    def run(n_frames, threads):
+    def prepare(n_frames):
         idx = [i % frames_avail for i in range(n_frames)]
-        block = np.ascontiguousarray(pts_host[idx])
-        sec, _ = ob.timed_frames(block, points, [eye] * n_frames, [T_end[i] for i in idx], [stamps[i] for i in idx], threads)
-        return n_frames * points / sec / 1e6, sec
+        return np.ascontiguousarray(pts_host[idx]), [eye] * n_frames, [T_end[i] for i in idx], [stamps[i] for i in idx]
 
-    single_mpts, t1 = run(1, 1)
+    def run(prepared, threads, eng=None):
+        block, ts, te, st = prepared
+        sec, _ = (eng or engine).timed_frames(block, points, ts, te, st, threads)  # seconds inside the C++ thread pool only
+        return len(ts) * points / sec / 1e6, sec
+
+    one = prepare(1)
+    single_mpts, t1 = run(one, 1)
     if steps is None:  # cpu_baseline object of the b200 arm: one bounded all-core sample
         n_frames = int(min(max(cores, cores * target_seconds / max(t1, 1e-3)), 4096))
-        all_mpts, sec = run(n_frames, cores)
-        out = {"value": round(all_mpts, 4), "unit": UNIT, "cores": cores, "kind": "port",
+        all_mpts, sec = run(prepare(n_frames), cores)
+        out = {"value": round(all_mpts, 4), "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{n_frames} scans x {points} pts of the same synthetic workload, one scan per task over {cores} "
-                         f"std::threads, {sec:.1f} s wall; oracle/kmc_oracle.cpp (-O3, double, reference's per-point Log/SVD/inverse kept)",
+                         f"std::threads, {sec:.1f} s wall; {what}",
                "single_thread_value": round(single_mpts, 4)}
+        if use_ref:  # the restatement beside it, same single-thread sample
+            out["oracle_port_single_thread_value"] = round(run(one, 1, ob)[0], 4)
         if gpu_out_host is not None:
-            worst = 0.0
+            worst = worst_ref = 0.0
             k = min(16, frames_avail)  # SURVEY 8d config 3: spot-check 16 frames of the benchmark data
             for f in range(k):
+                got = gpu_out_host[f][::8, :3].astype(np.float64)
                 ref = ob.deskew_xyzi_scan(pts_host[f][::8], eye, T_end[f], 0.0, 0.1, 0.05)
-                worst = max(worst, float(np.abs(gpu_out_host[f][::8, :3].astype(np.float64) - ref[:, :3]).max()))
+                worst = max(worst, float(np.abs(got - ref[:, :3]).max()))
+                if use_ref:
+                    ref2 = rb.deskew_xyzi_scan(pts_host[f][::8], eye, T_end[f], 0.0, 0.1, 0.05)
+                    worst_ref = max(worst_ref, float(np.abs(got - ref2[:, :3]).max()))
             out["gpu_vs_oracle_max_abs_err_m"] = worst
+            if use_ref:
+                out["gpu_vs_reference_sources_max_abs_err_m"] = worst_ref
             out["gpu_vs_oracle_frames"] = k
         return out
     # reference arm: `steps` timed steps, each a bounded sample of `cores` scans spread over all host threads
     per_step = cores
+    prepared = prepare(per_step)
     for _ in range(warmup):
-        run(per_step, cores)
-    t0 = time.perf_counter()
+        run(prepared, cores)
+    elapsed = 0.0
     for _ in range(steps):
-        run(per_step, cores)
-    elapsed = time.perf_counter() - t0
-    return {"value": per_step * points * steps / elapsed / 1e6, "elapsed": elapsed, "cores": cores, "per_step": per_step,
-            "single_thread_value": single_mpts}
+        elapsed += run(prepared, cores)[1]
+    res = {"value": per_step * points * steps / elapsed / 1e6, "elapsed": elapsed, "cores": cores, "per_step": per_step,
+           "single_thread_value": single_mpts, "kind": kind, "what": what}
+    if use_ref:
+        res["oracle_port_value"] = run(prepared, cores, ob)[0]
+    return res
 
 
 def numpy_scans(n_scans: int, points: int, rings: int, seed: int) -> np.ndarray:
@@ -239,15 +266,18 @@ def run_reference(args):
     if pts is None:
         pts = numpy_scans(n_sample, args.points, args.rings, SEED)
     res = cpu_baseline_leg(pts, xi, args.points, None, args.cpu_seconds, steps=args.steps, warmup=args.warmup)
-    sample = (f"each step = {res['per_step']} scans x {args.points} pts (one per host thread) of the same synthetic workload; "
-              f"oracle/kmc_oracle.cpp port of the reference's MotionCompensateFrame (the reference itself needs Eigen3/OpenCV, absent)")
+    sample = (f"each step = {res['per_step']} scans x {args.points} pts (one per host thread) of the same synthetic workload, "
+              f"timed inside the C++ thread pool; {res['what']}")
+    cpu = {"value": round(res["value"], 4), "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": sample,
+           "single_thread_value": round(res["single_thread_value"], 4)}
+    if "oracle_port_value" in res:
+        cpu["oracle_port_value"] = round(res["oracle_port_value"], 4)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(res["value"], 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * res["elapsed"] / max(args.steps, 1), 3),
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "points_per_scan": args.points, "sample": sample},
-        "cpu_baseline": {"value": round(res["value"], 4), "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample,
-                         "single_thread_value": round(res["single_thread_value"], 4)},
+        "cpu_baseline": cpu,
         "e2e": {"value": round(res["value"], 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

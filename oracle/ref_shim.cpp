@@ -1,5 +1,6 @@
-// ref_shim.cpp — C entry points over the UNMODIFIED reference sources, compiled only by `make -C oracle ref` on a box
-// that has <Eigen/Dense> (this image does not, so this file has never been compiled here — see DESIGN.md §5).
+// ref_shim.cpp — C entry points over the UNMODIFIED reference sources, compiled only by `make -C oracle ref`:
+// against Eigen 3 where <Eigen/Dense> exists, otherwise (this image) against ref_stub/Eigen/Dense, which forwards to
+// this repository's eigen_shim.hpp — see DESIGN.md §5 for what that does and does not prove.
 // It exposes the same two calls as libkmc_oracle.so so that tests/bench can swap the restatement for the real thing:
 //   kmc_ref_deskew_xyzi_scan   = KittiPclLoader conversion + kmc::GetPseudoTimeStamps + kmc::MotionCompensateFrame
 //   kmc_ref_timed_frames       = the same over many scans on std::threads, timed
@@ -17,6 +18,8 @@
 #include <stdexcept>
 
 #include "kitti_motion_compensation/data_io.hpp"
+#include "kitti_motion_compensation/lie_algebra.hpp"
+#include "kitti_motion_compensation/trajectory_interpolation.hpp"
 
 // trajectory_interpolation.cpp:21-25 (the Oxts constructor) references kmc::OxtsToPose, which lives in data_io.cpp
 // together with the OpenCV image loaders and is therefore not compiled into oracle/_ref.  The deskew path never takes
@@ -29,8 +32,10 @@ namespace {
 
 kmc::Affine3d FromColMajor(const double* m) {
   kmc::Affine3d T{kmc::Affine3d::Identity()};
-  for (int c = 0; c < 4; ++c)
-    for (int r = 0; r < 3; ++r) T.matrix()(r, c) = m[c * 4 + r];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) T.linear()(r, c) = m[c * 4 + r];
+    T.translation()(r) = m[12 + r];
+  }
   return T;
 }
 
@@ -54,6 +59,94 @@ kmc::Pointcloud Deskew(const float* xyzi, int64_t n, const double* T_start, cons
 
 extern "C" {
 
+// ---- the primitives of the path, one entry point per reference function (same shapes as the kmc_oracle_* calls) ----
+static void Mat3Out(Eigen::Matrix3d const& m, double* out) {
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) out[c * 3 + r] = m(r, c);
+}
+static Eigen::Matrix3d Mat3In(const double* in) {
+  Eigen::Matrix3d m;
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) m(r, c) = in[c * 3 + r];
+  return m;
+}
+static void AffineOut(kmc::Affine3d const& T, double* out) {
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r) out[c * 4 + r] = T.matrix()(r, c);
+}
+
+const char* kmc_ref_eigen_provider(void) {
+#ifdef EIGEN_WORLD_VERSION
+  return "eigen3";
+#else
+  return "shim";
+#endif
+}
+
+void kmc_ref_hat(const double phi[3], double out[9]) { Mat3Out(kmc::lie::Hat(Eigen::Vector3d{phi[0], phi[1], phi[2]}), out); }
+void kmc_ref_vee(const double m[9], double out[3]) {
+  Eigen::Vector3d const v{kmc::lie::Vee(Mat3In(m))};
+  for (int i = 0; i < 3; ++i) out[i] = v(i);
+}
+void kmc_ref_so3_exp(const double phi[3], double out[9]) { Mat3Out(kmc::lie::Exp(Eigen::Vector3d{phi[0], phi[1], phi[2]}), out); }
+void kmc_ref_so3_log(const double R[9], double out[3]) {
+  Eigen::Vector3d const v{kmc::lie::Log(Mat3In(R))};
+  for (int i = 0; i < 3; ++i) out[i] = v(i);
+}
+void kmc_ref_left_jacobian(const double phi[3], double out[9]) {
+  Mat3Out(kmc::lie::LeftJacobian(Eigen::Vector3d{phi[0], phi[1], phi[2]}), out);
+}
+void kmc_ref_inverse_left_jacobian(const double phi[3], double out[9]) {
+  Mat3Out(kmc::lie::InverseLeftJacobian(Eigen::Vector3d{phi[0], phi[1], phi[2]}), out);
+}
+void kmc_ref_se3_exp(const double xi[6], double out[16]) {
+  kmc::Twist t;
+  for (int i = 0; i < 6; ++i) t(i) = xi[i];
+  AffineOut(kmc::lie::Exp(t), out);
+}
+void kmc_ref_se3_log(const double T[16], double xi[6]) {
+  kmc::Twist const t{kmc::lie::Log(FromColMajor(T))};
+  for (int i = 0; i < 6; ++i) xi[i] = t(i);
+}
+// The reference aborts on a time outside [t1, t2] (trajectory_interpolation.cpp:32); callers check the range first.
+void kmc_ref_pose_at_time(double t1, const double P1[16], double t2, const double P2[16], double t, double out[16]) {
+  kmc::TrajectoryInterpolator const interp(t1, FromColMajor(P1), t2, FromColMajor(P2));
+  AffineOut(interp.GetPoseAtTime(t), out);
+}
+void kmc_ref_relative_pose_between_times(double t1, const double P1[16], double t2, const double P2[16], double anchor,
+                                         double query, double out[16]) {
+  kmc::TrajectoryInterpolator const interp(t1, FromColMajor(P1), t2, FromColMajor(P2));
+  AffineOut(interp.RelativePoseBetweenTimes(anchor, query), out);
+}
+double kmc_ref_fraction_of_scan_completed(const double p[4]) {
+  return kmc::FractionOfScanCompleted(kmc::Vector4d{p[0], p[1], p[2], p[3]});
+}
+double kmc_ref_pseudo_time_stamp(const double p[4], double start, double end) {
+  return kmc::GetPseudoTimeStamp(kmc::Vector4d{p[0], p[1], p[2], p[3]}, start, end);
+}
+void kmc_ref_motion_compensate_point(double t1, const double P1[16], double t2, const double P2[16], double point_stamp,
+                                     const double p[4], double requested_time, double out[4]) {
+  kmc::TrajectoryInterpolator const interp(t1, FromColMajor(P1), t2, FromColMajor(P2));
+  kmc::Vector4d const r{kmc::MotionCompensatePoint(interp, point_stamp, kmc::Vector4d{p[0], p[1], p[2], p[3]}, requested_time)};
+  for (int i = 0; i < 4; ++i) out[i] = r(i);
+}
+// MotionCompensateFrame on the reference's own layout: column-major n x 4 cloud + n stamps -> column-major n x 4.
+void kmc_ref_motion_compensate_frame(const double* cloud_colmajor, const double* stamps, int64_t n, const double T_start[16],
+                                     const double T_end[16], double t0, double t2, double t_req, double* out_colmajor) {
+  kmc::Pointcloud cloud{kmc::MatrixX4d(n, 4)};
+  kmc::VectorXd ts{kmc::VectorXd(n)}, intensities{kmc::VectorXd(n)};
+  for (int64_t i = 0; i < n; ++i) {
+    for (int c = 0; c < 4; ++c) cloud(i, c) = cloud_colmajor[c * n + i];
+    ts(i) = stamps[i];
+    intensities(i) = 0.0;
+  }
+  kmc::LidarScan const scan{t0, t_req, t2, cloud, intensities, ts};
+  kmc::Frame const frame(FromColMajor(T_start), FromColMajor(T_end), scan);
+  kmc::Pointcloud const res{kmc::MotionCompensateFrame(frame, t_req)};
+  for (int64_t i = 0; i < n; ++i)
+    for (int c = 0; c < 4; ++c) out_colmajor[c * n + i] = res(i, c);
+}
+
 int kmc_ref_deskew_xyzi_scan(const float* xyzi, int64_t n, const double* T_start, const double* T_end, double t0, double t2,
                              double t_req, double* out_xyz1) {
   kmc::Pointcloud const res{Deskew(xyzi, n, T_start, T_end, t0, t2, t_req)};
@@ -73,7 +166,8 @@ double kmc_ref_timed_frames(const float* xyzi, int64_t points_per_frame, int32_t
       if (f >= n_frames) break;
       kmc::Pointcloud const res{Deskew(xyzi + static_cast<int64_t>(f) * points_per_frame * 4, points_per_frame, T_start + 16 * f,
                                        T_end + 16 * f, stamps3[3 * f], stamps3[3 * f + 1], stamps3[3 * f + 2])};
-      acc += res.sum();
+      for (kmc::Index i = 0; i < res.rows(); ++i)
+        for (int c = 0; c < 4; ++c) acc += res(i, c);
     }
     partial[static_cast<size_t>(tid)] = acc;
   };

@@ -2,11 +2,12 @@
 //
 // The reference's public API carries Eigen types (include/kitti_motion_compensation/data_types.hpp:3,14,25-31 in the
 // reference repo).  When <Eigen/Dense> is installed the drop-in headers use the real thing; when it is not (this
-// image), this file supplies just enough of namespace Eigen — column-major fixed-size matrices, MatrixX4d, VectorXd,
+// image), this file supplies just enough of namespace Eigen — column-major fixed-size matrices, MatrixX4d / MatrixX3d, VectorXd,
 // Affine3d, AngleAxisd, comma initialisers — for the reference's call sites and test bodies to compile unchanged.
 // It is a data carrier, not a linear-algebra library: the numerics of the path live behind the C ABI (kmc_b200.h).
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cassert>
 #include <cmath>
@@ -261,23 +262,28 @@ class VectorXd {
   std::vector<double> v_;
 };
 
-// Dynamic-rows x 4, COLUMN-major — kmc::Pointcloud (x column, y column, z column, homogeneous column).
-class MatrixX4d {
+template <int R>
+class DynColsMatrix;
+
+// Dynamic-rows x C, COLUMN-major.  C = 4 is kmc::Pointcloud (x column, y column, z column, homogeneous column); C = 3 is
+// the pixel matrix of the reference's camera model (camera_model.cpp:9).
+template <int C>
+class DynRowsMatrix {
  public:
   class RowRef {
    public:
     RowRef(double* base, Index stride) : base_(base), stride_(stride) {}
-    RowRef& operator=(const Vector4d& v) {
-      for (int c = 0; c < 4; ++c) base_[c * stride_] = v(c);
+    RowRef& operator=(const Matrix<double, C, 1>& v) {
+      for (int c = 0; c < C; ++c) base_[c * stride_] = v(c);
       return *this;
     }
     RowRef& operator=(const RowRef& o) {
-      for (int c = 0; c < 4; ++c) base_[c * stride_] = o(c);
+      for (int c = 0; c < C; ++c) base_[c * stride_] = o(c);
       return *this;
     }
     double& operator()(Index c) { return base_[c * stride_]; }
     double operator()(Index c) const { return base_[c * stride_]; }
-    Index size() const { return 4; }
+    Index size() const { return C; }
 
    private:
     double* base_;
@@ -287,25 +293,102 @@ class MatrixX4d {
    public:
     ConstRowRef(const double* base, Index stride) : base_(base), stride_(stride) {}
     double operator()(Index c) const { return base_[c * stride_]; }
-    Index size() const { return 4; }
+    Index size() const { return C; }
 
    private:
     const double* base_;
     Index stride_;
   };
+  // one column; .array() is the identity (the shim has no separate array world)
+  class ConstColView {
+   public:
+    ConstColView(const double* base, Index n) : base_(base), n_(n) {}
+    double operator()(Index i) const { return base_[i]; }
+    Index size() const { return n_; }
+    const ConstColView& array() const { return *this; }
 
-  MatrixX4d() = default;
-  MatrixX4d(Index rows, Index cols) : rows_(rows), v_(static_cast<size_t>(rows * 4), 0.0) {
-    assert(cols == 4);
+   private:
+    const double* base_;
+    Index n_;
+  };
+  // m.array().colwise() / m.col(j).array(): every column divided element-wise by one column (camera_model.cpp:12)
+  class ColwiseView {
+   public:
+    explicit ColwiseView(const DynRowsMatrix& m) : m_(m) {}
+    DynRowsMatrix operator/(const ConstColView& d) const {
+      assert(d.size() == m_.rows());
+      DynRowsMatrix r(m_.rows(), C);
+      for (int c = 0; c < C; ++c)
+        for (Index i = 0; i < m_.rows(); ++i) r(i, c) = m_(i, c) / d(i);
+      return r;
+    }
+
+   private:
+    const DynRowsMatrix& m_;
+  };
+  class ArrayView {
+   public:
+    explicit ArrayView(const DynRowsMatrix& m) : m_(m) {}
+    ColwiseView colwise() const { return ColwiseView(m_); }
+
+   private:
+    const DynRowsMatrix& m_;
+  };
+  // the first k columns, read-only and assignable flavours (a.leftCols(3) = b.leftCols(3), camera_model.cpp:64)
+  class ConstLeftColsView {
+   public:
+    ConstLeftColsView(const DynRowsMatrix& m, Index k) : m_(m), k_(k) {}
+    Index rows() const { return m_.rows(); }
+    Index cols() const { return k_; }
+    double operator()(Index r, Index c) const { return m_(r, c); }
+
+   private:
+    const DynRowsMatrix& m_;
+    Index k_;
+  };
+  class LeftColsView {
+   public:
+    LeftColsView(DynRowsMatrix& m, Index k) : m_(m), k_(k) {}
+    LeftColsView& operator=(const ConstLeftColsView& o) {
+      assert(o.rows() == m_.rows() && o.cols() == k_);
+      for (Index c = 0; c < k_; ++c)
+        for (Index r = 0; r < m_.rows(); ++r) m_(r, c) = o(r, c);
+      return *this;
+    }
+
+   private:
+    DynRowsMatrix& m_;
+    Index k_;
+  };
+
+  DynRowsMatrix() = default;
+  DynRowsMatrix(Index rows, Index cols) : rows_(rows), v_(static_cast<size_t>(rows * C), 0.0) {
+    assert(cols == C);
     (void)cols;
   }
+  static DynRowsMatrix Ones(Index rows, Index cols) {
+    DynRowsMatrix m(rows, cols);
+    std::fill(m.v_.begin(), m.v_.end(), 1.0);
+    return m;
+  }
+  static DynRowsMatrix Zero(Index rows, Index cols) { return DynRowsMatrix(rows, cols); }
   Index rows() const { return rows_; }
-  Index cols() const { return 4; }
-  Index size() const { return rows_ * 4; }
+  Index cols() const { return C; }
+  Index size() const { return rows_ * C; }
   double& operator()(Index r, Index c) { return v_[static_cast<size_t>(c * rows_ + r)]; }
   double operator()(Index r, Index c) const { return v_[static_cast<size_t>(c * rows_ + r)]; }
   RowRef row(Index r) { return RowRef(v_.data() + r, rows_); }
   ConstRowRef row(Index r) const { return ConstRowRef(v_.data() + r, rows_); }
+  ConstColView col(Index c) const { return ConstColView(v_.data() + c * rows_, rows_); }
+  ArrayView array() const { return ArrayView(*this); }
+  LeftColsView leftCols(Index k) { return LeftColsView(*this, k); }
+  ConstLeftColsView leftCols(Index k) const { return ConstLeftColsView(*this, k); }
+  DynColsMatrix<C> transpose() const;
+  double sum() const {
+    double s = 0;
+    for (double x : v_) s += x;
+    return s;
+  }
   double* data() { return v_.data(); }
   const double* data() const { return v_.data(); }
 
@@ -313,6 +396,57 @@ class MatrixX4d {
   Index rows_ = 0;
   std::vector<double> v_;
 };
+
+// R x dynamic-columns, COLUMN-major: what `cloud.transpose()` is, so that `T * cloud.transpose()` reads as in the reference.
+template <int R>
+class DynColsMatrix {
+ public:
+  DynColsMatrix() = default;
+  DynColsMatrix(Index rows, Index cols) : cols_(cols), v_(static_cast<size_t>(R * cols), 0.0) {
+    assert(rows == R);
+    (void)rows;
+  }
+  Index rows() const { return R; }
+  Index cols() const { return cols_; }
+  double& operator()(Index r, Index c) { return v_[static_cast<size_t>(c * R + r)]; }
+  double operator()(Index r, Index c) const { return v_[static_cast<size_t>(c * R + r)]; }
+  DynRowsMatrix<R> transpose() const {
+    DynRowsMatrix<R> t(cols_, R);
+    for (Index c = 0; c < cols_; ++c)
+      for (int r = 0; r < R; ++r) t(c, r) = (*this)(r, c);
+    return t;
+  }
+
+ private:
+  Index cols_ = 0;
+  std::vector<double> v_;
+};
+
+template <int C>
+DynColsMatrix<C> DynRowsMatrix<C>::transpose() const {
+  DynColsMatrix<C> t(C, rows_);
+  for (Index r = 0; r < rows_; ++r)
+    for (int c = 0; c < C; ++c) t(c, r) = (*this)(r, c);
+  return t;
+}
+
+// (M x K) * (K x n)
+template <int M, int K>
+DynColsMatrix<M> operator*(const Matrix<double, M, K>& a, const DynColsMatrix<K>& b) {
+  DynColsMatrix<M> r(M, b.cols());
+  for (Index j = 0; j < b.cols(); ++j)
+    for (int i = 0; i < M; ++i) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) acc += a(i, k) * b(k, j);
+      r(i, j) = acc;
+    }
+  return r;
+}
+
+using MatrixX4d = DynRowsMatrix<4>;
+using MatrixX3d = DynRowsMatrix<3>;
+using Matrix4Xd = DynColsMatrix<4>;
+using Matrix3Xd = DynColsMatrix<3>;
 
 class AngleAxisd {
  public:
@@ -406,6 +540,16 @@ class Affine3d {
   Vector4d operator*(const Vector4d& p) const {
     Vector3d const q = linear_ * Vector3d{p(0), p(1), p(2)} + translation_ * p(3);
     return Vector4d{q(0), q(1), q(2), p(3)};
+  }
+  // 4 x n block of homogeneous columns: top rows L v3 + t w, the bottom row passes through
+  Matrix4Xd operator*(const Matrix4Xd& p) const {
+    Matrix4Xd r(4, p.cols());
+    for (Index j = 0; j < p.cols(); ++j) {
+      for (int i = 0; i < 3; ++i)
+        r(i, j) = linear_(i, 0) * p(0, j) + linear_(i, 1) * p(1, j) + linear_(i, 2) * p(2, j) + translation_(i) * p(3, j);
+      r(3, j) = p(3, j);
+    }
+    return r;
   }
   Affine3d& operator*=(const Matrix3d& m) {
     linear_ = linear_ * m;

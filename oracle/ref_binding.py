@@ -48,6 +48,19 @@ def lib() -> C.CDLL:
         _lib.kmc_ref_deskew_xyzi_scan.argtypes = [_fp, C.c_int64, _dp, _dp, C.c_double, C.c_double, C.c_double, _dp]
         _lib.kmc_ref_timed_frames.restype = C.c_double
         _lib.kmc_ref_timed_frames.argtypes = [_fp, C.c_int64, C.c_int32, _dp, _dp, _dp, C.c_int32, _dp]
+        _lib.kmc_ref_oxts_to_pose.argtypes = [_dp, C.c_double, _dp]
+        _lib.kmc_ref_make_frame_poses.argtypes = [_dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp]
+        _lib.kmc_ref_interpolate_trajectory.argtypes = [_dp, _dp, C.c_double, _dp]
+        _lib.kmc_ref_load_time_stamp.restype = C.c_double
+        _lib.kmc_ref_load_time_stamp.argtypes = [C.c_char_p, C.c_int64]
+        _lib.kmc_ref_load_oxts.argtypes = [C.c_char_p, C.c_int64, _dp]
+        _lib.kmc_ref_load_pointcloud.restype = C.c_int64
+        _lib.kmc_ref_load_pointcloud.argtypes = [C.c_char_p, _dp, _dp, C.c_int64]
+        _lib.kmc_ref_write_pointcloud.argtypes = [C.c_char_p, C.c_int64, _dp, _dp, C.c_int64]
+        _lib.kmc_ref_motion_compensate_run.restype = C.c_double
+        _lib.kmc_ref_motion_compensate_run.argtypes = [C.c_char_p]
+        _lib.kmc_ref_project_pointcloud_on_frame.argtypes = [_dp, C.c_int64, _dp, _dp, _dp, C.POINTER(C.POINTER(C.c_int32)),
+                                                             C.POINTER(_dp), C.POINTER(C.c_int64)]
     return _lib
 
 
@@ -183,3 +196,79 @@ def timed_frames(xyzi_f32, points_per_frame, T_start, T_end, stamps3, n_threads)
     sec = lib().kmc_ref_timed_frames(pts.ctypes.data_as(_fp), points_per_frame, n_frames, _ptr(ts), _ptr(te),
                                      _ptr(st.reshape(-1)), n_threads, C.byref(chk))
     return sec, chk.value
+
+
+# ---- data_io.cpp / handlers.cpp (the rows either side of the path) -------------------------------------------------
+def oxts_to_pose(oxts7, scale=1.0):
+    """OxtsToPose (data_io.cpp:68-88); oxts7 = [stamp, lat, lon, alt, roll, pitch, yaw]."""
+    out = np.empty(16)
+    lib().kmc_ref_oxts_to_pose(_ptr(_d(oxts7)), scale, _ptr(out))
+    return _from_colmajor(out, 4)
+
+
+def interpolate_trajectory(o1, o2, t):
+    _check(o1[0], o2[0], t)
+    out = np.empty(16)
+    lib().kmc_ref_interpolate_trajectory(_ptr(_d(o1)), _ptr(_d(o2)), t, _ptr(out))
+    return _from_colmajor(out, 4)
+
+
+def make_frame_poses(o_prev, o_cur, o_next, stamp_start, stamp_end):
+    """MakeFrame (data_io.cpp:253-269) -> (T_start, T_end)."""
+    _check(o_prev[0], o_cur[0], stamp_start)
+    _check(o_cur[0], o_next[0], stamp_end)
+    a, b = np.empty(16), np.empty(16)
+    lib().kmc_ref_make_frame_poses(_ptr(_d(o_prev)), _ptr(_d(o_cur)), _ptr(_d(o_next)), stamp_start, stamp_end, _ptr(a), _ptr(b))
+    return _from_colmajor(a, 4), _from_colmajor(b, 4)
+
+
+def load_time_stamp(path, frame_id):
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)  # the reference prints and exit(0)s
+    return lib().kmc_ref_load_time_stamp(os.fsencode(path), frame_id)
+
+
+def load_oxts(run_folder, frame_id):
+    out = np.empty(7)
+    lib().kmc_ref_load_oxts(os.fsencode(run_folder), frame_id, _ptr(out))
+    return out
+
+
+def load_pointcloud(path):
+    """KittiPclLoader::LoadPointcloud (data_io.cpp:101-138) -> ((n,4) double cloud x y z 1, (n,) double intensities)."""
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)  # the reference throws std::runtime_error, which would cross the C boundary
+    n = os.path.getsize(path) // 16
+    cloud, inten = np.empty((n, 4)), np.empty(n)
+    got = lib().kmc_ref_load_pointcloud(os.fsencode(path), _ptr(cloud), _ptr(inten), n)
+    assert got == n
+    return cloud, inten
+
+
+def write_pointcloud(folder, frame_id, cloud_n4, intensities):
+    cloud = _d(np.asarray(cloud_n4, dtype=np.float64).reshape(-1, 4))
+    inten = _d(intensities)
+    lib().kmc_ref_write_pointcloud(os.fsencode(folder), frame_id, _ptr(cloud), _ptr(inten), cloud.shape[0])
+
+
+def motion_compensate_run(run_folder) -> float:
+    """handlers.cpp:41-65 on a KITTI run folder; returns wall seconds.  The caller guarantees the folder is well formed
+    (the reference exit(0)s / aborts on missing files and out-of-range stamps)."""
+    return lib().kmc_ref_motion_compensate_run(os.fsencode(run_folder))
+
+
+def project_pointcloud_on_frame(cloud_n4, tf_c00_lo, R_rect_00, P_rects):
+    """ProjectPointcloudOnFrame (camera_model.cpp:38-95) with cv::circle recording instead of drawing.
+    P_rects: four 3x4 matrices (cameras 00..03).  Returns, per camera, (uv int32 (m,2), colour (m,3)) of the points the
+    reference draws, in point order (max_range = the reference's default 15 m)."""
+    cloud = np.asarray(cloud_n4, dtype=np.float64)
+    n = cloud.shape[0]
+    P = np.ascontiguousarray(np.stack([np.asarray(p, dtype=np.float64).T.reshape(-1) for p in P_rects]))  # 4 x 12, column-major each
+    uv = [np.empty((n, 2), dtype=np.int32) for _ in range(4)]
+    col = [np.empty((n, 3)) for _ in range(4)]
+    uv_ptrs = (C.POINTER(C.c_int32) * 4)(*[a.ctypes.data_as(C.POINTER(C.c_int32)) for a in uv])
+    col_ptrs = (_dp * 4)(*[_ptr(a) for a in col])
+    counts = (C.c_int64 * 4)()
+    lib().kmc_ref_project_pointcloud_on_frame(_ptr(_colmajor(cloud)), n, _ptr(_colmajor(tf_c00_lo)), _ptr(_colmajor(R_rect_00)), _ptr(P),
+                                              uv_ptrs, col_ptrs, counts)
+    return [(uv[k][:counts[k]].copy(), col[k][:counts[k]].copy()) for k in range(4)]

@@ -15,18 +15,15 @@
 #include "kitti_motion_compensation/motion_compensation.hpp"
 #include "kitti_motion_compensation/timestamp_mocking.hpp"
 
+#include <cstring>
 #include <stdexcept>
+#include <string>
 
+#include "kitti_motion_compensation/camera_model.hpp"
 #include "kitti_motion_compensation/data_io.hpp"
+#include "kitti_motion_compensation/handlers.hpp"
 #include "kitti_motion_compensation/lie_algebra.hpp"
 #include "kitti_motion_compensation/trajectory_interpolation.hpp"
-
-// trajectory_interpolation.cpp:21-25 (the Oxts constructor) references kmc::OxtsToPose, which lives in data_io.cpp
-// together with the OpenCV image loaders and is therefore not compiled into oracle/_ref.  The deskew path never takes
-// that constructor; this definition only satisfies the dynamic linker.
-namespace kmc {
-Eigen::Affine3d OxtsToPose(Oxts const&, double const) { throw std::logic_error("OxtsToPose is not part of oracle/_ref"); }
-}  // namespace kmc
 
 namespace {
 
@@ -180,6 +177,104 @@ double kmc_ref_timed_frames(const float* xyzi, int64_t points_per_frame, int32_t
   for (double p : partial) total += p;
   if (checksum) *checksum = total;
   return std::chrono::duration<double>(b - a).count();
+}
+
+
+// ---- data_io.cpp / handlers.cpp: the rows either side of the path --------------------------------
+static kmc::Oxts OxtsFrom7(const double o[7]) { return kmc::Oxts{o[0], o[1], o[2], o[3], o[4], o[5], o[6], 0.0, 0.0, 0.0}; }
+
+void kmc_ref_oxts_to_pose(const double oxts7[7], double scale, double out[16]) { AffineOut(kmc::OxtsToPose(OxtsFrom7(oxts7), scale), out); }
+
+// MakeFrame (data_io.cpp:253-269): start / end pose of a scan from the three surrounding OxTS packets.  Aborts (the
+// reference's assert) when a scan stamp lies outside its packet interval — callers check first.
+void kmc_ref_make_frame_poses(const double o_prev[7], const double o_cur[7], const double o_next[7], double stamp_start,
+                              double stamp_end, double T_start[16], double T_end[16]) {
+  kmc::LidarScan scan{};
+  scan.stamp_start = stamp_start;
+  scan.stamp_middle = 0.5 * (stamp_start + stamp_end);
+  scan.stamp_end = stamp_end;
+  kmc::Frame const frame{kmc::MakeFrame(OxtsFrom7(o_prev), OxtsFrom7(o_cur), OxtsFrom7(o_next), scan)};
+  AffineOut(frame.T_start, T_start);
+  AffineOut(frame.T_end, T_end);
+}
+
+void kmc_ref_interpolate_trajectory(const double o1[7], const double o2[7], double t, double out[16]) {
+  AffineOut(kmc::trajectory_interpolation::InterpolateTrajectory(OxtsFrom7(o1), OxtsFrom7(o2), t), out);
+}
+
+double kmc_ref_load_time_stamp(const char* file, int64_t frame_id) { return kmc::LoadTimeStamp(kmc::Path(file), static_cast<size_t>(frame_id)); }
+
+void kmc_ref_load_oxts(const char* run_folder, int64_t frame_id, double out7[7]) {
+  kmc::Oxts const o{kmc::LoadOxts(kmc::Path(run_folder), static_cast<size_t>(frame_id))};
+  double const v[7] = {o.stamp, o.lat, o.lon, o.alt, o.roll, o.pitch, o.yaw};
+  std::memcpy(out7, v, sizeof v);
+}
+
+// KittiPclLoader::LoadPointcloud (data_io.cpp:101-138): returns the number of points; fills at most `capacity` rows of
+// out_xyz1 (row-major n x 4 doubles) and out_intensity.  Pass capacity 0 to only count.
+int64_t kmc_ref_load_pointcloud(const char* file, double* out_xyz1, double* out_intensity, int64_t capacity) {
+  kmc::KittiPclLoader loader;
+  auto const [cloud, intensities] = loader.LoadPointcloud(kmc::Path(file));
+  int64_t const n = cloud.rows();
+  for (int64_t i = 0; i < n && i < capacity; ++i) {
+    for (int c = 0; c < 4; ++c) out_xyz1[4 * i + c] = cloud(i, c);
+    out_intensity[i] = intensities(i);
+  }
+  return n;
+}
+
+// WritePointcloud (data_io.cpp:287-313) of a row-major n x 4 double cloud + intensities.
+void kmc_ref_write_pointcloud(const char* folder, int64_t frame_id, const double* xyz1, const double* intensity, int64_t n) {
+  kmc::Pointcloud cloud{kmc::MatrixX4d(n, 4)};
+  kmc::VectorXd in{kmc::VectorXd(n)};
+  for (int64_t i = 0; i < n; ++i) {
+    for (int c = 0; c < 4; ++c) cloud(i, c) = xyz1[4 * i + c];
+    in(i) = intensity[i];
+  }
+  kmc::WritePointcloud(kmc::Path(folder), static_cast<size_t>(frame_id), cloud, in);
+}
+
+// handlers.cpp:41-65 on a KITTI run folder; returns the wall time in seconds.
+double kmc_ref_motion_compensate_run(const char* run_folder) {
+  auto const a = std::chrono::steady_clock::now();
+  kmc::MotionCompensateRun(kmc::Path(run_folder));
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+}
+
+// ---- camera_model.cpp:38-95 + :5-36 ---------------------------------------------------------------
+// ProjectPointcloudOnFrame on a column-major n x 4 cloud.  cv::circle is the recording stub of ref_stub/opencv2, so what
+// comes back is the reference's own draw list per camera: integer pixel centres and the three colour channels, in call
+// order.  uv_out[k] holds 2 ints and color_out[k] 3 doubles per drawn point (capacity n each); counts[k] = points drawn.
+void kmc_ref_project_pointcloud_on_frame(const double* cloud_colmajor, int64_t n, const double tf_c00_lo[16],
+                                         const double R_rect_00[9], const double P_rect[4][12], int32_t* const uv_out[4],
+                                         double* const color_out[4], int64_t counts[4]) {
+  kmc::LidarScan scan{};
+  scan.cloud = kmc::MatrixX4d(n, 4);
+  for (int64_t i = 0; i < n; ++i)
+    for (int c = 0; c < 4; ++c) scan.cloud(i, c) = cloud_colmajor[c * n + i];
+  scan.intensities = kmc::VectorXd(n);
+  scan.timestamps = kmc::VectorXd(n);
+  kmc::Image const blank{0.0, cv::Mat(375, 1242)};
+  kmc::Frame const frame(kmc::Affine3d::Identity(), kmc::Affine3d::Identity(), scan, kmc::Images{blank, blank, blank, blank});
+  kmc::viz::CameraCalibrations calib{};
+  kmc::viz::CameraCalibration* cams[4] = {&calib.camera_00, &calib.camera_01, &calib.camera_02, &calib.camera_03};
+  for (int k = 0; k < 4; ++k) {
+    cams[k]->R_rect = Eigen::Matrix3d::Identity();
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) cams[k]->P_rect(r, c) = P_rect[k][c * 3 + r];  // column-major 3 x 4
+  }
+  calib.camera_00.R_rect = Mat3In(R_rect_00);
+  kmc::Images const drawn{kmc::viz::ProjectPointcloudOnFrame(frame, calib, FromColMajor(tf_c00_lo))};
+  kmc::Image const* imgs[4] = {&drawn.image_00, &drawn.image_01, &drawn.image_02, &drawn.image_03};
+  for (int k = 0; k < 4; ++k) {
+    auto const& list = imgs[k]->image.drawn;
+    counts[k] = static_cast<int64_t>(list.size());
+    for (size_t j = 0; j < list.size(); ++j) {
+      uv_out[k][2 * j] = list[j].center.x;
+      uv_out[k][2 * j + 1] = list[j].center.y;
+      for (int c = 0; c < 3; ++c) color_out[k][3 * j + c] = list[j].color.val[c];
+    }
+  }
 }
 
 }  // extern "C"

@@ -114,3 +114,52 @@ def closed_form_deskew(xyzi: np.ndarray, xi: np.ndarray, x_req: float, frac: np.
 
 def max_abs_err(out_xyzi: np.ndarray, ref_xyz1: np.ndarray) -> float:
     return float(np.max(np.abs(out_xyzi[:, :3].astype(np.float64) - ref_xyz1[:, :3])))
+
+
+# ---- KITTI run folders (the layout handlers.cpp:41-65 / data_io.cpp:18-66,140-166 read) -------------------------------------
+def _clock(t: float) -> str:
+    """seconds since midnight -> '2011-09-26 HH:MM:SS.nnnnnnnnn' (parsed by utils.cpp:34-41)."""
+    h, rem = divmod(t, 3600.0)
+    m, s = divmod(rem, 60.0)
+    return f"2011-09-26 {int(h):02d}:{int(m):02d}:{s:012.9f}"
+
+
+def make_run_folder(root: str, n_frames: int = 6, points: int = 20_000, seed: int = 1, yaw_rate: float = 0.3,
+                    speed: float = 11.0, ragged: bool = True) -> dict:
+    """Writes a synthetic KITTI raw run (oxts/, velodyne_points/{data,timestamps*.txt}) under `root` and returns what was
+    written.  10 Hz scans, OxTS packets at the middle of each scan, a vehicle driving a curve (speed m/s, yaw_rate rad/s).
+    Scans are chosen so that the reference's own range assert cannot fire (every pseudo stamp stays inside its scan)."""
+    rng = np.random.default_rng(seed)
+    os.makedirs(os.path.join(root, "oxts", "data"), exist_ok=True)
+    os.makedirs(os.path.join(root, "velodyne_points", "data"), exist_ok=True)
+    t0 = 13 * 3600 + 4 * 60 + 32.0
+    starts, middles, ends, scans, oxts = [], [], [], [], []
+    lat, lon, yaw = 49.011212804408, 8.4228850417969, -1.2219096732051
+    for i in range(n_frames):
+        starts.append(t0 + 0.1 * i + rng.uniform(0, 1e-3))
+        ends.append(starts[-1] + 0.1033 + rng.uniform(-1e-3, 1e-3))
+        middles.append(0.5 * (starts[-1] + ends[-1]) + rng.uniform(-1e-4, 1e-4))
+        n = points + (int(rng.integers(-points // 10, points // 10)) if ragged else 0)
+        pts = synthetic_scan(n, 64, seed * 1000 + i)
+        # keep the reference away from its own abort: drop points whose pseudo stamp would round outside the scan
+        frac = (np.pi - np.arctan2(pts[:, 1].astype(np.float64), pts[:, 0].astype(np.float64))) / (2 * np.pi)
+        st = starts[-1] + frac * (ends[-1] - starts[-1])
+        pts = pts[(st >= starts[-1]) & (st <= ends[-1])]
+        scans.append(pts)
+        pts.tofile(os.path.join(root, "velodyne_points", "data", f"{i:010d}.bin"))
+        o = [lat, lon, 112.8 + 0.01 * i, 0.02 + 0.001 * i, 1e-3 * i, yaw]
+        oxts.append(o)
+        with open(os.path.join(root, "oxts", "data", f"{i:010d}.txt"), "w") as f:
+            f.write(" ".join(f"{v:.13g}" for v in o) + " 0 0 " + f"{speed} 0 0 " + " ".join(["0"] * 14) + " 4 10 4 4 0\n")
+        lat += speed * 0.1 * np.sin(yaw + np.pi / 2) / 111_000.0 * 0.5
+        lon += speed * 0.1 * np.cos(yaw) / 73_000.0
+        yaw += yaw_rate * 0.1
+    for name, vals in (("velodyne_points/timestamps_start.txt", starts), ("velodyne_points/timestamps.txt", middles),
+                       ("velodyne_points/timestamps_end.txt", ends), ("oxts/timestamps.txt", middles)):
+        with open(os.path.join(root, name), "w") as f:
+            f.write("\n".join(_clock(t) for t in vals) + "\n")
+    return {"starts": starts, "middles": middles, "ends": ends, "scans": scans, "oxts": oxts}
+
+
+def read_bin(path: str) -> np.ndarray:
+    return np.fromfile(path, dtype=np.float32).reshape(-1, 4)

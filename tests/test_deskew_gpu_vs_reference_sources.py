@@ -91,3 +91,100 @@ def test_time_from_w_mode(capi, oracle, cuda):
     stamps = np.clip(t0 + frac.astype(np.float64) * (t2 - t0), t0, t2)
     ref = rb.motion_compensate_frame(cloud, stamps, T_start, T_end, t0, t2, t_req)
     assert helpers.max_abs_err(out, ref) < TOL_M
+
+
+# ---- the projection kernels against the reference's own draw list ------------------------------------------
+def _draw_list_parity(planes, drawn):
+    """planes[k]: (n,4) float32 (u, v, z, colour | -1) from the kernel; drawn[k]: (uv int32 (m,2), colour (m,3)) recorded from
+    the reference's cv::circle calls.  The set of drawn points may differ only where a point sits within 1e-4 m of a culling
+    threshold; integer pixels may differ only within 0.02 px of a pixel edge (fp32 vs double)."""
+    for k in range(4):
+        out = planes[k]
+        ref_uv, ref_col = drawn[k]
+        keep = out[:, 3] >= 0
+        assert abs(int(keep.sum()) - len(ref_uv)) <= 2, (int(keep.sum()), len(ref_uv))
+        if int(keep.sum()) != len(ref_uv):
+            continue  # a threshold-straddling point: sequence alignment is lost, the per-camera oracle test covers the rest
+        got = out[keep]
+        du = np.abs(np.floor(got[:, 0]).astype(np.int64) - ref_uv[:, 0]) + np.abs(np.floor(got[:, 1]).astype(np.int64) - ref_uv[:, 1])
+        # cv::Point truncates toward zero; floor == trunc for the non-negative pixels of on-image points
+        on_image = (ref_uv[:, 0] >= 0) & (ref_uv[:, 0] < 1242) & (ref_uv[:, 1] >= 0) & (ref_uv[:, 1] < 375)
+        edge = np.minimum(got[:, :2] % 1.0, 1.0 - got[:, :2] % 1.0).min(axis=1) < 0.02
+        assert on_image.sum() > 1000
+        assert np.all(du[on_image & ~edge] == 0), f"camera {k}: integer pixels differ away from pixel edges"
+        assert np.all(du[on_image] <= 1)
+        assert np.abs(got[:, 3] - ref_col[:, 1]).max() < 1e-3
+
+
+def test_four_camera_projection_matches_the_reference_draw_list(capi, cuda):
+    from test_projection import calibration
+    torch = cuda
+    T, R_rect, P = calibration()
+    names = ("00", "01", "02", "03")
+    cams = [capi.camera_params_from_calibration(P[k], R_rect, T, 15.0) for k in names]
+    pts = helpers.real_scan()
+    n = len(pts)
+    d_in = torch.from_numpy(pts).cuda()
+    planes = [torch.empty_like(d_in) for _ in range(4)]
+    capi.deskew_project_frame4_device(d_in.data_ptr(), 0, [p.data_ptr() for p in planes], n, None, cams, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    cloud = np.concatenate([pts[:, :3].astype(np.float64), np.ones((n, 1))], axis=1)
+    _draw_list_parity([p.cpu().numpy() for p in planes], rb.project_pointcloud_on_frame(cloud, T, R_rect, [P[k] for k in names]))
+
+
+def test_fused_deskew_projection_matches_reference_deskew_then_project(capi, cuda):
+    """handlers.cpp:83-87: MotionCompensateFrame, then ProjectPointcloudOnFrame of the result — both from the compiled
+    reference — against ONE fused kernel launch."""
+    from test_projection import calibration
+    torch = cuda
+    T, R_rect, P = calibration()
+    names = ("00", "01", "02", "03")
+    cams = [capi.camera_params_from_calibration(P[k], R_rect, T, 15.0) for k in names]
+    pts = helpers.real_scan()
+    n = len(pts)
+    T_start, T_end, t0, t1, t2 = helpers.config1_frame()
+    params = capi.frame_params_from_poses(T_start, T_end, t0, t2, t1)
+    d_in = torch.from_numpy(pts).cuda()
+    cloud_out = torch.empty_like(d_in)
+    planes = [torch.empty_like(d_in) for _ in range(4)]
+    capi.deskew_project_frame4_device(d_in.data_ptr(), cloud_out.data_ptr(), [p.data_ptr() for p in planes], n, params, cams, 0,
+                                      torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref_cloud = rb.deskew_xyzi_scan(pts, T_start, T_end, t0, t2, t1)
+    assert_parity(cloud_out.cpu().numpy(), ref_cloud, pts)
+    _draw_list_parity([p.cpu().numpy() for p in planes], rb.project_pointcloud_on_frame(ref_cloud, T, R_rect, [P[k] for k in names]))
+
+
+# ---- SURVEY 8f ranks 1-3: a whole run, the reference's MotionCompensateRun against the drop-in's --------------------------------
+def test_motion_compensate_run_matches_the_reference_handler(capi, cuda, tmp_path):
+    """The same synthetic KITTI run folder through handlers.cpp:41-65 compiled from the reference (CPU) and through this
+    repository's motion_compensate_runs CLI (libkitti_motion_compensation_lib.so -> CUDA): every middle frame within
+    1e-5 m (both sides write float32), intensities and frame 0 byte-identical.  The last file differs ON PURPOSE: the
+    reference writes the first frame's cloud under the last id (handlers.cpp:36-38), the drop-in writes the last frame's."""
+    import os
+    import shutil
+    import subprocess
+    from kitti_motion_compensation_b200 import build
+    n = 9
+    ref_dir, our_dir = tmp_path / "ref" / "run_sync", tmp_path / "ours" / "run_sync"
+    info = helpers.make_run_folder(str(ref_dir), n, 30_000, seed=6)
+    shutil.copytree(ref_dir, our_dir)
+    rb.motion_compensate_run(str(ref_dir))
+    cli = build.build_example()
+    r = subprocess.run([cli, str(tmp_path / "ours"), "run_sync"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = 0.0
+    for i in range(n):
+        a = helpers.read_bin(str(ref_dir / "velodyne_points" / "data_motion_compensated" / f"{i:010d}.bin"))
+        b = helpers.read_bin(str(our_dir / "velodyne_points" / "data_motion_compensated" / f"{i:010d}.bin"))
+        if i == n - 1:
+            assert np.array_equal(a, info["scans"][0]) and np.array_equal(b, info["scans"][n - 1])
+            continue
+        assert a.shape == b.shape and np.array_equal(a[:, 3], b[:, 3])
+        if i == 0:
+            assert np.array_equal(a, b)
+        else:
+            worst = max(worst, float(np.abs(a[:, :3].astype(np.float64) - b[:, :3]).max()))
+            assert np.abs(a[:, :3] - info["scans"][i][:, :3]).max() > 0.05
+    print(f"run of {n} frames: max |dxyz| between the reference's files and the drop-in's = {worst:.3e} m")
+    assert worst < TOL_M

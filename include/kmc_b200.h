@@ -250,6 +250,35 @@ KMC_B200_API int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* xy
 KMC_B200_API int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out,
                              const kmc_b200_frame_params* params, int64_t* n_points_out);
 
+/* Many KITTI .bin files in one overlapped pass: files are packed in order into groups that fit one staging slot of the
+ * handle (so create the handle with a capacity of several scans), and three slots rotate through
+ * read -> H2D -> batched kernel -> D2H -> write with io_threads readers and writers (<= 0: min(8, host threads)).
+ * This is the loop body of MotionCompensateRun (handlers.cpp:55-64: LoadSingleFrame + MotionCompensateFrame +
+ * WritePointcloud per frame) for n_files frames at once; params[f] belongs to paths_in[f].  points_out (optional)
+ * receives the number of points of every file.  A file larger than the handle's capacity is KMC_B200_ERR_CAPACITY. */
+KMC_B200_API int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* const* paths_in,
+                                           const char* const* paths_out, const kmc_b200_frame_params* params, int time_mode,
+                                           int32_t io_threads, int64_t* points_out);
+
+typedef struct kmc_b200_run_stats {
+  int64_t frames;           /* files found in velodyne_points/data */
+  int64_t frames_deskewed;  /* frames 1 .. n-2 */
+  int64_t points_deskewed;
+  double seconds_prepare;   /* listing, time stamps, OxTS packets, poses, per-frame records */
+  double seconds_pipeline;  /* kmc_b200_deskew_bin_files */
+  double seconds_total;
+} kmc_b200_run_stats;
+
+/* MotionCompensateRun (handlers.cpp:41-65) on a KITTI raw run folder: reads oxts/timestamps.txt, every oxts/data packet and
+ * velodyne_points/{timestamps_start,timestamps,timestamps_end}.txt once, builds every frame's start/end pose as MakeFrame
+ * does (data_io.cpp:253-269), deskews frames 1 .. n-2 to their camera-trigger time through kmc_b200_deskew_bin_files into
+ * velodyne_points/data_motion_compensated/, and copies frames 0 and n-1 through unchanged (the reference writes frame 0's
+ * cloud under the last id, handlers.cpp:36-38; here the last file is the last frame's own cloud).  Missing or malformed
+ * files are KMC_B200_ERR_IO; a scan stamp outside its OxTS interval — where the reference asserts — is
+ * KMC_B200_ERR_TIME_OUT_OF_RANGE.  stats may be NULL. */
+KMC_B200_API int kmc_b200_motion_compensate_run(kmc_b200_handle* h, const char* run_folder, int32_t io_threads,
+                                                kmc_b200_run_stats* stats);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

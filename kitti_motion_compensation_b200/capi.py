@@ -52,6 +52,12 @@ FRAME_PARAMS_DTYPE = np.dtype([
 assert FRAME_PARAMS_DTYPE.itemsize == C.sizeof(FrameParams) == 64
 
 
+class RunStats(C.Structure):
+    """kmc_b200_run_stats"""
+    _fields_ = [("frames", C.c_int64), ("frames_deskewed", C.c_int64), ("points_deskewed", C.c_int64),
+                ("seconds_prepare", C.c_double), ("seconds_pipeline", C.c_double), ("seconds_total", C.c_double)]
+
+
 class KmcError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"kmc_b200 status {status} ({message})")
@@ -111,6 +117,9 @@ SIGNATURES = {
     "kmc_b200_pseudo_time_stamps_xy_host": (C.c_int, [_vp, _dp, _dp, C.c_int64, C.c_double, C.c_double, _dp]),
     "kmc_b200_project_frame_host": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(CameraParams)]),
     "kmc_b200_deskew_bin_file": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.POINTER(FrameParams), C.POINTER(C.c_int64)]),
+    "kmc_b200_deskew_bin_files": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _vp, C.c_int, C.c_int32,
+                                            C.POINTER(C.c_int64)]),
+    "kmc_b200_motion_compensate_run": (C.c_int, [_vp, C.c_char_p, C.c_int32, _vp]),
 }
 
 _lib = None
@@ -382,6 +391,25 @@ class Handle:
         n = C.c_int64()
         check(lib().kmc_b200_deskew_bin_file(self._h, path_in.encode(), path_out.encode(), C.byref(params), C.byref(n)))
         return n.value
+
+    def deskew_bin_files(self, paths_in: list[str], paths_out: list[str], params: np.ndarray, mode: int = TIME_FROM_AZIMUTH,
+                         io_threads: int = 0) -> np.ndarray:
+        """Many .bin files through one overlapped read -> H2D -> kernel -> D2H -> write pipeline; returns points per file."""
+        prm = np.ascontiguousarray(params, dtype=FRAME_PARAMS_DTYPE)
+        n = len(paths_in)
+        assert len(paths_out) == n and prm.size == n
+        a = (C.c_char_p * n)(*[os.fsencode(p) for p in paths_in])
+        b = (C.c_char_p * n)(*[os.fsencode(p) for p in paths_out])
+        points = np.zeros(n, dtype=np.int64)
+        check(lib().kmc_b200_deskew_bin_files(self._h, n, a, b, prm.ctypes.data, mode, io_threads,
+                                              points.ctypes.data_as(C.POINTER(C.c_int64))))
+        return points
+
+    def motion_compensate_run(self, run_folder: str, io_threads: int = 0) -> dict:
+        """MotionCompensateRun (handlers.cpp:41-65) on a KITTI raw run folder; returns the kmc_b200_run_stats fields."""
+        stats = RunStats()
+        check(lib().kmc_b200_motion_compensate_run(self._h, os.fsencode(run_folder), io_threads, C.byref(stats)))
+        return {name: getattr(stats, name) for name, _ in RunStats._fields_}
 
 
 def deskew_batch_multi_gpu(handles: list[Handle], xyzi: np.ndarray, offsets: np.ndarray, params: np.ndarray,

@@ -3,10 +3,19 @@
 // ends in a kernel launch from kmc_kernels.cu or an error status.
 #include <cuda_runtime.h>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -14,6 +23,7 @@
 
 #include "kmc_b200.h"
 #include "kmc_host_math.hpp"
+#include "kmc_internal.hpp"
 #include "kmc_kernels.cuh"
 
 // NVTX ranges around the host entry points (visible in Nsight Systems / Compute timelines); header-only, no cost when
@@ -50,6 +60,12 @@ int Fail(int status, const std::string& what) {
   t_last_error = what;
   return status;
 }
+
+}  // namespace
+namespace kmc_b200::internal {
+int SetError(int status, const std::string& what) { return Fail(status, what); }
+}  // namespace kmc_b200::internal
+namespace {
 
 int FailCuda(cudaError_t e, const char* where) {
   t_last_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
@@ -802,6 +818,227 @@ int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char
   bool const closed = (std::fclose(g) == 0);
   if (static_cast<int64_t>(put) != n || !closed) return Fail(KMC_B200_ERR_IO, std::string("short write: ") + path_out);
   if (n_points_out) *n_points_out = n;
+  return KMC_B200_OK;
+}
+
+
+// ---- many KITTI .bin files through one overlapped pipeline ------------------------------------------------------------------
+namespace {
+
+// Runs fn(0..n_items-1) on up to n_threads short-lived host threads; returns the first non-zero status.
+int ParallelFor(int64_t n_items, int n_threads, const std::function<int(int64_t)>& fn) {
+  if (n_items <= 0) return KMC_B200_OK;
+  n_threads = static_cast<int>(std::min<int64_t>(std::max(n_threads, 1), n_items));
+  std::atomic<int64_t> next{0};
+  std::atomic<int> status{KMC_B200_OK};
+  std::string message;
+  std::mutex message_mu;
+  auto body = [&] {
+    for (;;) {
+      int64_t const i = next.fetch_add(1);
+      if (i >= n_items || status.load() != KMC_B200_OK) return;
+      int const rc = fn(i);
+      if (rc != KMC_B200_OK) {
+        std::lock_guard<std::mutex> lock(message_mu);
+        if (status.load() == KMC_B200_OK) {
+          message = t_last_error;  // Fail() wrote it on this worker thread
+          status.store(rc);
+        }
+      }
+    }
+  };
+  if (n_threads == 1) {
+    body();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(body);
+    for (auto& th : pool) th.join();
+  }
+  if (status.load() != KMC_B200_OK) t_last_error = message;
+  return status.load();
+}
+
+int ReadWholeFile(const char* path, void* dst, size_t bytes) {
+  int const fd = ::open(path, O_RDONLY | O_CLOEXEC);
+  if (fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path);
+  size_t done = 0;
+  while (done < bytes) {
+    ssize_t const got = ::pread(fd, static_cast<char*>(dst) + done, bytes - done, static_cast<off_t>(done));
+    if (got < 0 && errno == EINTR) continue;
+    if (got <= 0) break;
+    done += static_cast<size_t>(got);
+  }
+  ::close(fd);
+  if (done != bytes) return Fail(KMC_B200_ERR_IO, std::string("short read: ") + path);
+  return KMC_B200_OK;
+}
+
+int WriteWholeFile(const char* path, const void* src, size_t bytes) {
+  int const fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+  if (fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to create output file: ") + path);
+  size_t done = 0;
+  while (done < bytes) {
+    ssize_t const put = ::pwrite(fd, static_cast<const char*>(src) + done, bytes - done, static_cast<off_t>(done));
+    if (put < 0 && errno == EINTR) continue;
+    if (put <= 0) break;
+    done += static_cast<size_t>(put);
+  }
+  bool const closed = (::close(fd) == 0);
+  if (done != bytes || !closed) return Fail(KMC_B200_ERR_IO, std::string("short write: ") + path);
+  return KMC_B200_OK;
+}
+
+}  // namespace
+
+// Files are packed, in order, into groups that fit one staging slot of the handle.  Three slots rotate through
+//   read (io_threads x pread straight into the slot's pinned input buffer)  ->  H2D  ->  batched deskew kernel  ->  D2H
+//   ->  write (io_threads x pwrite straight from the slot's pinned output buffer),
+// the calling thread doing the reads and the launches, one helper thread retiring slots (event wait + writes), so the
+// disk / page cache, both PCIe directions and the SMs are busy at the same time.  No intermediate host copies: the .bin
+// format is the kernel's input layout.
+int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* const* paths_in, const char* const* paths_out,
+                              const kmc_b200_frame_params* params, int mode, int32_t io_threads, int64_t* points_out) {
+  TraceRange const trace("kmc_b200_deskew_bin_files");
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_files: null handle");
+  if (n_files < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_bin_files: negative n_files");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_bin_files: unknown time mode");
+  if (n_files == 0) return KMC_B200_OK;
+  if (!paths_in || !paths_out || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_files: null argument");
+  if (io_threads <= 0) io_threads = static_cast<int32_t>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())));
+  constexpr int kSlots = kmc_b200_handle::kSlots;
+
+  // sizes, global offsets, groups
+  std::vector<int64_t> offsets(static_cast<size_t>(n_files) + 1, 0);
+  for (int32_t f = 0; f < n_files; ++f) {
+    if (!paths_in[f] || !paths_out[f]) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_files: null path");
+    struct stat st;
+    if (::stat(paths_in[f], &st) != 0) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + paths_in[f]);
+    if (st.st_size % 16 != 0)
+      return Fail(KMC_B200_ERR_IO, std::string("KITTI pointcloud binary file is not a whole number of xyzi points: ") + paths_in[f]);
+    int64_t const n = static_cast<int64_t>(st.st_size / 16);
+    if (n > h->capacity)
+      return Fail(KMC_B200_ERR_CAPACITY, std::string("scan larger than the handle's capacity (create the handle with more points): ") + paths_in[f]);
+    offsets[static_cast<size_t>(f) + 1] = offsets[static_cast<size_t>(f)] + n;
+    if (points_out) points_out[f] = n;
+  }
+  struct Group {
+    int32_t first_file, end_file;
+  };
+  std::vector<Group> groups;
+  for (int32_t f = 0; f < n_files;) {
+    int32_t e = f + 1;
+    while (e < n_files && offsets[static_cast<size_t>(e) + 1] - offsets[static_cast<size_t>(f)] <= h->capacity) ++e;
+    groups.push_back({f, e});
+    f = e;
+  }
+  int64_t const n_total = offsets[static_cast<size_t>(n_files)];
+
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  if (int rc = EnsureTables(h, n_files)) return rc;
+  KMC_CUDA_TRY(cudaMemcpyAsync(h->d_offsets, offsets.data(), offsets.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream[0]));
+  KMC_CUDA_TRY(cudaMemcpyAsync(h->d_params, params, static_cast<size_t>(n_files) * sizeof(kmc_b200_frame_params), cudaMemcpyHostToDevice, h->stream[0]));
+  KMC_CUDA_TRY(cudaStreamSynchronize(h->stream[0]));
+
+  // slot hand-over between the submitting (this) thread and the retiring thread
+  std::mutex mu;
+  std::condition_variable cv;
+  bool slot_free[kSlots];
+  for (bool& b : slot_free) b = true;
+  std::deque<size_t> submitted;  // group indices in submission order
+  bool no_more = false;
+  int retire_status = KMC_B200_OK;
+  std::string retire_message;
+
+  std::thread retirer([&] {
+    cudaSetDevice(h->device);
+    for (;;) {
+      size_t g;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !submitted.empty() || no_more; });
+        if (submitted.empty()) return;
+        g = submitted.front();
+        submitted.pop_front();
+      }
+      int const slot = static_cast<int>(g % kSlots);
+      int rc = KMC_B200_OK;
+      cudaError_t const e = cudaEventSynchronize(h->done[slot]);
+      if (e != cudaSuccess) rc = FailCuda(e, "cudaEventSynchronize(done)");
+      if (rc == KMC_B200_OK) {
+        Group const grp = groups[g];
+        int64_t const base = offsets[static_cast<size_t>(grp.first_file)];
+        rc = ParallelFor(grp.end_file - grp.first_file, io_threads, [&](int64_t k) -> int {
+          size_t const f = static_cast<size_t>(grp.first_file + k);
+          return WriteWholeFile(paths_out[f], h->h_out[slot] + 4 * (offsets[f] - base), static_cast<size_t>(offsets[f + 1] - offsets[f]) * 16);
+        });
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (rc != KMC_B200_OK && retire_status == KMC_B200_OK) {
+          retire_status = rc;
+          retire_message = t_last_error;
+        }
+        slot_free[slot] = true;
+      }
+      cv.notify_all();
+    }
+  });
+
+  int status = KMC_B200_OK;
+  for (size_t g = 0; g < groups.size() && status == KMC_B200_OK; ++g) {
+    int const slot = static_cast<int>(g % kSlots);
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return slot_free[slot]; });
+      if (retire_status != KMC_B200_OK) break;
+      slot_free[slot] = false;
+    }
+    Group const grp = groups[g];
+    int64_t const base = offsets[static_cast<size_t>(grp.first_file)];
+    int64_t const count = offsets[static_cast<size_t>(grp.end_file)] - base;
+    status = ParallelFor(grp.end_file - grp.first_file, io_threads, [&](int64_t k) -> int {
+      size_t const f = static_cast<size_t>(grp.first_file + k);
+      return ReadWholeFile(paths_in[f], h->h_in[slot] + 4 * (offsets[f] - base), static_cast<size_t>(offsets[f + 1] - offsets[f]) * 16);
+    });
+    auto submit = [&]() -> int {
+      if (count > 0) {
+        size_t const bytes = static_cast<size_t>(count) * 16;
+        KMC_CUDA_TRY(cudaMemcpyAsync(h->d_in[slot], h->h_in[slot], bytes, cudaMemcpyHostToDevice, h->stream[slot]));
+        auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
+        KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[slot], h->d_out[slot], h->d_offsets, h->d_params, n_files, count, base,
+                                                      n_total, mode, cfg, h->sm_count, h->stream[slot]));
+        KMC_CUDA_TRY(cudaMemcpyAsync(h->h_out[slot], h->d_out[slot], bytes, cudaMemcpyDeviceToHost, h->stream[slot]));
+      }
+      KMC_CUDA_TRY(cudaEventRecord(h->done[slot], h->stream[slot]));
+      return KMC_B200_OK;
+    };
+    if (status == KMC_B200_OK) status = submit();
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (status == KMC_B200_OK) submitted.push_back(g);
+      else slot_free[slot] = true;
+    }
+    cv.notify_all();
+  }
+  std::string const keep = t_last_error;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    no_more = true;
+  }
+  cv.notify_all();
+  retirer.join();
+  if (status != KMC_B200_OK) {
+    for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
+    cudaGetLastError();
+    t_last_error = keep;
+    return status;
+  }
+  if (retire_status != KMC_B200_OK) {
+    t_last_error = retire_message;
+    return retire_status;
+  }
   return KMC_B200_OK;
 }
 

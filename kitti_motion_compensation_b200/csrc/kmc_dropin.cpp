@@ -17,8 +17,10 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "kitti_motion_compensation/camera_model.hpp"
@@ -381,72 +383,35 @@ KMC_EXPORT void CopyOverUncompensatedFirstAndLastFrame(Path const run_folder) {
   }
 }
 
-namespace {
-
-std::vector<float> ReadBin(Path const& file) {
-  std::ifstream in{file, std::ios::in | std::ios::binary | std::ios::ate};
-  if (!in.is_open()) throw std::runtime_error("Unable to open requested KITTI pointcloud binary file: " + file.string());
-  std::int64_t const bytes{static_cast<std::int64_t>(in.tellg())};
-  if (bytes < 0 || bytes % 16 != 0) throw std::runtime_error("Opened KITTI pointcloud binary file is incorrectly formatted: " + file.string());
-  std::vector<float> data(static_cast<size_t>(bytes / 4));
-  in.seekg(0, std::ios::beg);
-  in.read(reinterpret_cast<char*>(data.data()), bytes);
-  return data;
-}
-
-}  // namespace
-
-// The reference handles one frame at a time (load three oxts packets, load + expand the scan, deskew, write).  Here a
-// run is processed in groups of up to kRunGroupFrames frames: the scans of a group are concatenated in their on-disk
-// float32 form and go through ONE pipelined batched pass (kmc_b200_deskew_batch_host), then every file is written.
+// The reference handles one frame at a time (load three oxts packets, load + expand the scan, deskew, write).  Here the
+// whole run goes through kmc_b200_motion_compensate_run: text files read once, scans streamed disk -> pinned memory ->
+// GPU -> pinned memory -> disk in groups of ~16 with reads, copies, kernels and writes overlapped.  The handle for runs
+// is separate from the per-frame default handle because its staging slots hold a group of scans, not one.
 KMC_EXPORT void MotionCompensateRun(Path const run_folder) {
-  namespace fs = std::filesystem;
-  constexpr size_t kRunGroupFrames = 256;  // ~0.5 GB of scans per direction
-  Path const velodyne{run_folder / Path{"velodyne_points"}};
-  size_t const n_frames{NumberOfFilesInDirectory(velodyne / Path("data"))};
-  Path const out_folder{velodyne / Path("data_motion_compensated")};
-  if (!fs::is_directory(out_folder)) fs::create_directory(out_folder);
-  CopyOverUncompensatedFirstAndLastFrame(run_folder);
-  if (n_frames < 3) return;
-
-  std::vector<Oxts> oxts;  // every packet once (the reference re-reads three per frame)
-  for (size_t i{0}; i < n_frames; ++i) oxts.push_back(LoadOxts(run_folder, i));
-  kmc_b200_handle* handle{DefaultHandle()};
-
-  for (size_t group_begin{1}; group_begin + 1 < n_frames; group_begin += kRunGroupFrames) {
-    size_t const group_end{std::min(group_begin + kRunGroupFrames, n_frames - 1)};
-    std::vector<float> scans;
-    std::vector<std::int64_t> offsets{0};
-    std::vector<kmc_b200_frame_params> params;
-    for (size_t i{group_begin}; i < group_end; ++i) {
-      Time const start{LoadTimeStamp(velodyne / Path("timestamps_start.txt"), i)};
-      Time const middle{LoadTimeStamp(velodyne / Path("timestamps.txt"), i)};  // camera trigger = requested time
-      Time const end{LoadTimeStamp(velodyne / Path("timestamps_end.txt"), i)};
-      Affine3d const T_start{trajectory_interpolation::InterpolateTrajectory(oxts[i - 1], oxts[i], start)};
-      Affine3d const T_end{trajectory_interpolation::InterpolateTrajectory(oxts[i], oxts[i + 1], end)};
-      double p1[16], p2[16];
-      ToBuffer(T_start, p1);
-      ToBuffer(T_end, p2);
-      kmc_b200_frame_params rec{};
-      int const rc = kmc_b200_frame_params_from_poses(p1, p2, start, end, middle, &rec);
-      if (rc == KMC_B200_ERR_TIME_OUT_OF_RANGE || rc == KMC_B200_ERR_EMPTY_INTERVAL) AbortOutOfRange("MotionCompensateRun", middle, start, end);
-      ThrowUnlessOk(rc, "kmc_b200_frame_params_from_poses");
-      params.push_back(rec);
-      std::vector<float> const scan{ReadBin(velodyne / Path("data") / (IdToZeroPaddedString(i) + ".bin"))};
-      scans.insert(scans.end(), scan.begin(), scan.end());
-      offsets.push_back(static_cast<std::int64_t>(scans.size() / 4));
-    }
-    std::vector<float> result(scans.size());
-    ThrowUnlessOk(kmc_b200_deskew_batch_host(handle, scans.data(), result.data(), offsets.data(), params.data(),
-                                             static_cast<std::int32_t>(params.size()), KMC_B200_TIME_FROM_AZIMUTH),
-                  "kmc_b200_deskew_batch_host");
-    for (size_t i{group_begin}; i < group_end; ++i) {
-      size_t const k{i - group_begin};
-      std::ofstream out(out_folder / (IdToZeroPaddedString(i) + ".bin"), std::ios::out | std::ios::binary);
-      out.write(reinterpret_cast<const char*>(result.data() + 4 * offsets[k]), static_cast<std::streamsize>(16 * (offsets[k + 1] - offsets[k])));
-      std::cout << "Motion compensated pointcloud number: " << i << std::endl;
-    }
+  constexpr std::int64_t kRunSlotPoints = 2'000'000;  // 32 MB per staging buffer, ~16 KITTI scans per group
+  static std::mutex mu;
+  static kmc_b200_handle* run_handle = nullptr;
+  static int run_handle_device = -1;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!run_handle || run_handle_device != g_device.load()) {
+    if (run_handle) kmc_b200_handle_destroy(run_handle);
+    run_handle = nullptr;
+    ThrowUnlessOk(kmc_b200_handle_create(g_device.load(), kRunSlotPoints, &run_handle), "kmc_b200_handle_create");
+    run_handle_device = g_device.load();
   }
+  kmc_b200_run_stats stats{};
+  int const rc = kmc_b200_motion_compensate_run(run_handle, run_folder.c_str(), 0, &stats);
+  if (rc == KMC_B200_ERR_TIME_OUT_OF_RANGE || rc == KMC_B200_ERR_EMPTY_INTERVAL) {
+    std::fprintf(stderr, "MotionCompensateRun: %s (the reference asserts here: trajectory_interpolation.cpp:32)\n", kmc_b200_last_error());
+    std::abort();
+  }
+  if (rc == KMC_B200_ERR_IO && std::string(kmc_b200_last_error()).rfind("failed to open timestamp file", 0) == 0) {
+    std::cout << kmc_b200_last_error() << '\n';
+    std::exit(0);  // the reference's convention for an unreadable time-stamp file (data_io.cpp:27-30)
+  }
+  ThrowUnlessOk(rc, "kmc_b200_motion_compensate_run");
+  for (std::int64_t i{1}; i + 1 < stats.frames; ++i) std::cout << "Motion compensated pointcloud number: " << i << '\n';
+  std::cout << std::flush;
 }
 
 // ---- calibration files + projection (camera_model.cpp, data_io.cpp:168-210,321-406) -----------------------------------------

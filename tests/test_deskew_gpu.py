@@ -681,3 +681,96 @@ def test_reference_layout_f64_entry_point(capi, oracle, cuda):
         # empty cloud
         out0, flags, rc = h.deskew_cloud_f64(np.zeros((0, 4)), np.zeros(0), t0, t2, t1, p)
         assert rc == capi.OK and out0.shape == (0, 4)
+
+
+# ---- many .bin files through the overlapped pipeline ---------------------------------------------------
+def test_bin_files_pipeline_matches_per_frame_calls(capi, oracle, cuda, tmp_path):
+    """kmc_b200_deskew_bin_files: ragged and empty files, more groups than staging slots (slot reuse), every output
+    bit-identical to the single-frame device call on the same points and within 1e-5 m of the oracle."""
+    rng = np.random.default_rng(41)
+    sizes = [5000, 0, 1, 12_345, 7, 9000, 0, 0, 4096, 15_999, 16_000, 3, 8000, 8000, 8000, 100, 11_111]
+    paths_in, paths_out, scans, frames = [], [], [], []
+    for k, n in enumerate(sizes):
+        pts = helpers.synthetic_scan(n, 64, 500 + k) if n else np.zeros((0, 4), dtype=np.float32)
+        scans.append(pts)
+        paths_in.append(str(tmp_path / f"in_{k:03d}.bin"))
+        paths_out.append(str(tmp_path / f"out_{k:03d}.bin"))
+        pts.tofile(paths_in[-1])
+        T_start = helpers.random_pose(rng, mercator=bool(k % 2))
+        frames.append((T_start, T_start @ oracle.se3_exp(helpers.random_twist(rng)), float(rng.choice([0.0, 0.02, 0.05, 0.1]))))
+    params = capi.params_array([capi.frame_params_from_poses(a, b, 0.0, 0.1, t) for a, b, t in frames])
+    with capi.Handle(0, 16_000) as h:   # at most two mid-size files per group -> ~10 groups over 3 slots
+        for threads in (1, 4):
+            for p in paths_out:
+                if os.path.exists(p):
+                    os.remove(p)
+            points = h.deskew_bin_files(paths_in, paths_out, params, io_threads=threads)
+            assert points.tolist() == sizes
+            for k, n in enumerate(sizes):
+                got = helpers.read_bin(paths_out[k])
+                assert got.shape == (n, 4)
+                if n == 0:
+                    continue
+                want = run_frame(cuda, capi, scans[k], capi.frame_params_from_poses(*frames[k][:2], 0.0, 0.1, frames[k][2]))
+                assert np.array_equal(got, want), f"file {k}"
+                if n >= 1000:
+                    a, b, t = frames[k]
+                    assert_parity(got[::5], oracle_frame(oracle, scans[k][::5], a, b, 0.0, 0.1, t), scans[k][::5])
+        # error behaviour: nothing is computed for a bad list
+        with pytest.raises(capi.KmcError) as e:
+            h.deskew_bin_files([str(tmp_path / "missing.bin")], [paths_out[0]], params[:1])
+        assert e.value.status == capi.ERR_IO
+        (tmp_path / "odd.bin").write_bytes(b"\0" * 20)
+        with pytest.raises(capi.KmcError) as e:
+            h.deskew_bin_files([str(tmp_path / "odd.bin")], [paths_out[0]], params[:1])
+        assert e.value.status == capi.ERR_IO
+        helpers.synthetic_scan(16_001, 64, 1).tofile(str(tmp_path / "big.bin"))
+        with pytest.raises(capi.KmcError) as e:
+            h.deskew_bin_files([str(tmp_path / "big.bin")], [paths_out[0]], params[:1])
+        assert e.value.status == capi.ERR_CAPACITY
+        with pytest.raises(capi.KmcError) as e:
+            h.deskew_bin_files(paths_in[:1], [str(tmp_path / "no_such_dir" / "x.bin")], params[:1])
+        assert e.value.status == capi.ERR_IO
+        assert h.deskew_bin_files([], [], params[:0]).size == 0
+
+
+def test_motion_compensate_run_c_abi(capi, oracle, cuda, tmp_path):
+    """kmc_b200_motion_compensate_run on a generated KITTI run: middle frames against the oracle with MakeFrame poses
+    (data_io.cpp:253-269), first and last frame copied through, stats filled, error statuses where the reference exits."""
+    n = 8
+    run = tmp_path / "2011_09_26_drive_0001_sync"
+    info = helpers.make_run_folder(str(run), n, 12_000, seed=9)
+    packets = [[info["middles"][i], *info["oxts"][i]] for i in range(n)]
+    with capi.Handle(0, 30_000) as h:
+        stats = h.motion_compensate_run(str(run))
+        assert stats["frames"] == n and stats["frames_deskewed"] == n - 2
+        assert stats["points_deskewed"] == sum(len(s) for s in info["scans"][1:-1])
+        assert stats["seconds_total"] >= stats["seconds_pipeline"] > 0
+        out = run / "velodyne_points" / "data_motion_compensated"
+        assert sorted(os.listdir(out)) == [f"{i:010d}.bin" for i in range(n)]
+        for i in range(1, n - 1):
+            T_start, T_end = oracle.make_frame_poses(packets[i - 1], packets[i], packets[i + 1], info["starts"][i], info["ends"][i])
+            want = oracle.deskew_xyzi_scan(info["scans"][i], T_start, T_end, info["starts"][i], info["ends"][i], info["middles"][i])
+            got = helpers.read_bin(str(out / f"{i:010d}.bin"))
+            assert_parity(got, want, info["scans"][i])
+        assert np.array_equal(helpers.read_bin(str(out / f"{0:010d}.bin")), info["scans"][0])
+        assert np.array_equal(helpers.read_bin(str(out / f"{n - 1:010d}.bin")), info["scans"][n - 1])
+        # a second call overwrites in place and gives the same files
+        before = [helpers.read_bin(str(out / f"{i:010d}.bin")) for i in range(n)]
+        h.motion_compensate_run(str(run), io_threads=2)
+        assert all(np.array_equal(before[i], helpers.read_bin(str(out / f"{i:010d}.bin"))) for i in range(n))
+        # missing time-stamp file / OxTS packet -> ERR_IO; scan stamp outside its OxTS interval -> ERR_TIME_OUT_OF_RANGE
+        os.rename(run / "oxts" / "data" / f"{3:010d}.txt", run / "oxts" / "data" / "hidden")
+        with pytest.raises(capi.KmcError) as e:
+            h.motion_compensate_run(str(run))
+        assert e.value.status == capi.ERR_IO
+        os.rename(run / "oxts" / "data" / "hidden", run / "oxts" / "data" / f"{3:010d}.txt")
+        lines = (run / "velodyne_points" / "timestamps_start.txt").read_text().splitlines()
+        lines[2] = helpers._clock(info["middles"][1] - 0.5)
+        (run / "velodyne_points" / "timestamps_start.txt").write_text("\n".join(lines) + "\n")
+        with pytest.raises(capi.KmcError) as e:
+            h.motion_compensate_run(str(run))
+        assert e.value.status == capi.ERR_TIME_OUT_OF_RANGE
+        with pytest.raises(capi.KmcError) as e:
+            h.motion_compensate_run(str(tmp_path / "nowhere"))
+        assert e.value.status == capi.ERR_IO

@@ -252,7 +252,7 @@ KMC_B200_API int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_i
 
 /* Many KITTI .bin files in one overlapped pass: files are packed in order into groups that fit one staging slot of the
  * handle (so create the handle with a capacity of several scans), and three slots rotate through
- * read -> H2D -> batched kernel -> D2H -> write with io_threads readers and writers (<= 0: min(8, host threads)).
+ * read -> H2D -> batched kernel -> D2H -> write with io_threads readers and writers (<= 0: min(16, host threads)).
  * This is the loop body of MotionCompensateRun (handlers.cpp:55-64: LoadSingleFrame + MotionCompensateFrame +
  * WritePointcloud per frame) for n_files frames at once; params[f] belongs to paths_in[f].  points_out (optional)
  * receives the number of points of every file.  A file larger than the handle's capacity is KMC_B200_ERR_CAPACITY. */

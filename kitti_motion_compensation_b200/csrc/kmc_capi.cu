@@ -904,7 +904,7 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
   if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_bin_files: unknown time mode");
   if (n_files == 0) return KMC_B200_OK;
   if (!paths_in || !paths_out || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_files: null argument");
-  if (io_threads <= 0) io_threads = static_cast<int32_t>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())));
+  if (io_threads <= 0) io_threads = static_cast<int32_t>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
   constexpr int kSlots = kmc_b200_handle::kSlots;
 
   // sizes, global offsets, groups

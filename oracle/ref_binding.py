@@ -1,6 +1,7 @@
-"""ctypes binding of oracle/_ref/libkmc_ref.so — the reference's OWN hot-path sources (motion_compensation.cpp,
-trajectory_interpolation.cpp, lie_algebra.cpp, timestamp_mocking.cpp), compiled unmodified from /root/reference by
-`make -C oracle ref` behind the C entry points of oracle/ref_shim.cpp.
+"""ctypes binding of oracle/_ref/libkmc_ref.so — the reference's OWN sources (motion_compensation.cpp,
+trajectory_interpolation.cpp, lie_algebra.cpp, timestamp_mocking.cpp of the hot path, plus data_io.cpp, handlers.cpp,
+camera_model.cpp and utils.cpp either side of it), compiled unmodified from /root/reference by `make -C oracle ref`
+behind the C entry points of oracle/ref_shim.cpp.  OpenCV is a stub whose cv::circle records a draw list.
 
 TEST INFRASTRUCTURE ONLY (same rule as oracle/binding.py): tests/, smoke() and bench.py's CPU legs may load it, the
 product never does.  The library is built in the development container (where /root/reference exists) and travels to

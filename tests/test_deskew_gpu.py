@@ -774,3 +774,26 @@ def test_motion_compensate_run_c_abi(capi, oracle, cuda, tmp_path):
         with pytest.raises(capi.KmcError) as e:
             h.motion_compensate_run(str(tmp_path / "nowhere"))
         assert e.value.status == capi.ERR_IO
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_bin_files_pipeline_stress(capi, cuda, tmp_path, seed):
+    """Randomised file sizes, slot capacities and thread counts, several passes over the same handle: the threaded
+    read / retire hand-over must give the batched device result bit for bit every time."""
+    rng = np.random.default_rng(seed)
+    n_files = int(rng.integers(20, 60))
+    sizes = [int(x) for x in rng.choice([0, 1, 17, 255, 256, 1000, 4097, 6000], n_files)]
+    scans = [helpers.synthetic_scan(n, 64, 900 + k) if n else np.zeros((0, 4), dtype=np.float32) for k, n in enumerate(sizes)]
+    paths_in = [str(tmp_path / f"i{k}.bin") for k in range(n_files)]
+    paths_out = [str(tmp_path / f"o{k}.bin") for k in range(n_files)]
+    for p, s in zip(paths_in, scans):
+        s.tofile(p)
+    params, _ = capi.synth_frame_params(n_files, 77 + seed, 0, 0.5)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    want = run_batch(cuda, capi, np.concatenate(scans), offsets, params)
+    for capacity, threads in ((6000, 1), (6001, 3), (13_000, 8), (100_000, 16)):
+        with capi.Handle(0, capacity) as h:
+            for _ in range(3):
+                h.deskew_bin_files(paths_in, paths_out, params, io_threads=threads)
+                got = np.concatenate([helpers.read_bin(p) for p in paths_out])
+                assert np.array_equal(got, want), (capacity, threads)

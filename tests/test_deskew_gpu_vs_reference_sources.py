@@ -106,12 +106,12 @@ def _draw_list_parity(planes, drawn):
         if int(keep.sum()) != len(ref_uv):
             continue  # a threshold-straddling point: sequence alignment is lost, the per-camera oracle test covers the rest
         got = out[keep]
-        du = np.abs(np.floor(got[:, 0]).astype(np.int64) - ref_uv[:, 0]) + np.abs(np.floor(got[:, 1]).astype(np.int64) - ref_uv[:, 1])
-        # cv::Point truncates toward zero; floor == trunc for the non-negative pixels of on-image points
+        # cv::Point(double, double) truncates toward zero (u = -0.15 is drawn at column 0)
+        du = np.abs(np.trunc(got[:, 0]).astype(np.int64) - ref_uv[:, 0]) + np.abs(np.trunc(got[:, 1]).astype(np.int64) - ref_uv[:, 1])
         on_image = (ref_uv[:, 0] >= 0) & (ref_uv[:, 0] < 1242) & (ref_uv[:, 1] >= 0) & (ref_uv[:, 1] < 375)
         # a coordinate error e (fp32 deskew: <= 1e-5 m) moves a pixel by ~ f e / z = 721 * 1e-5 / z px: compare integers for
         # points deeper than 0.5 m (< 0.015 px) that sit more than 0.05 px from a pixel edge
-        edge = np.minimum(got[:, :2] % 1.0, 1.0 - got[:, :2] % 1.0).min(axis=1) < 0.05
+        edge = np.minimum(np.abs(got[:, :2]) % 1.0, 1.0 - np.abs(got[:, :2]) % 1.0).min(axis=1) < 0.05
         deep = got[:, 2] > 0.5
         assert (on_image & deep & ~edge).sum() > 1000
         assert np.all(du[on_image & deep & ~edge] == 0), f"camera {k}: integer pixels differ away from pixel edges"

@@ -44,8 +44,19 @@ def main():
         print(json.dumps({"generated": run, "frames": args.frames, "points_deskewed_per_run": total_points,
                           "bytes_in": total_points * 16, "seconds": round(time.perf_counter() - t0, 2)}), flush=True)
         out_dir = os.path.join(run, "velodyne_points", "data_motion_compensated")
-        with capi.Handle(0, args.slot_points) as h:
-            h.motion_compensate_run(run)  # warm-up: page cache, CUDA context, first launches
+        a = time.perf_counter()
+        with capi.Handle(0, 1024):
+            pass
+        t_ctx = time.perf_counter() - a
+        a = time.perf_counter()
+        h = capi.Handle(0, args.slot_points)
+        t_handle = time.perf_counter() - a
+        print(json.dumps({"cuda_context_plus_small_handle_s": round(t_ctx, 3), "run_handle_create_s": round(t_handle, 3),
+                          "run_handle_bytes_pinned": 6 * args.slot_points * 16, "run_handle_bytes_device": 6 * args.slot_points * 16}), flush=True)
+        with h:
+            a = time.perf_counter()
+            h.motion_compensate_run(run)  # first call: cold launches
+            print(json.dumps({"arm": "kmc_b200_motion_compensate_run", "first_call_s": round(time.perf_counter() - a, 4)}), flush=True)
             for threads in [int(x) for x in args.io_threads.split(",")]:
                 best, stats_best = None, None
                 for _ in range(args.reps):
@@ -62,6 +73,15 @@ def main():
                                   "seconds_prepare": round(stats_best["seconds_prepare"], 4),
                                   "seconds_pipeline": round(stats_best["seconds_pipeline"], 4), "best_of": args.reps,
                                   "slot_points": args.slot_points, "dir": base}), flush=True)
+        # the whole process, as a user of the reference's CLI sees it (CUDA context + handle creation included)
+        import subprocess
+        from kitti_motion_compensation_b200 import build
+        cli = build.build_example()
+        shutil.rmtree(out_dir)
+        a = time.perf_counter()
+        r = subprocess.run([cli, work, os.path.basename(run)], capture_output=True, text=True)
+        print(json.dumps({"arm": "motion_compensate_runs CLI, one process", "returncode": r.returncode, "frames": args.frames,
+                          "seconds_wall": round(time.perf_counter() - a, 3)}), flush=True)
         # the reference's own handler on the first --ref-frames frames of the same run
         from oracle import ref_binding as rb
         if rb.available() and args.ref_frames >= 3:

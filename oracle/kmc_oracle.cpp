@@ -8,9 +8,12 @@
 //   (test/test_motion_compensation.cpp:54-76, test/test_timestamp_mocking.cpp:55-57,71-73,84-86,
 //    test/test_lie_algebra.cpp:5-47, test/test_trajectory_interpolation.cpp:43-60,
 //    test/test_oxts_to_pose.cpp:17-20) — see tests/test_oracle_golden.py.
-//   The reference ships NO golden for a frame with rotation != 0 and cannot be compiled in this image
-//   (Eigen3 / OpenCV / GTest absent), so rotating frames are pinned only through the Lie round-trip and
-//   artificial-pose interpolation tests above.
+//   The reference ships NO golden for a frame with rotation != 0 and its own build cannot run in this image
+//   (Eigen3 / OpenCV / GTest absent).  Rotating frames are therefore pinned against the reference's own eight
+//   source files compiled unmodified into oracle/_ref/libkmc_ref.so (`make -C oracle ref`: Eigen supplied by
+//   this repository's shim when Eigen 3 is missing, OpenCV by a recording stub) — function by function and end
+//   to end in tests/test_oracle_vs_reference_sources.py — and, independently of any shared code, against a
+//   40-digit matrix expm/logm evaluation in tests/test_oracle_golden.py.
 //
 // What is restated (file:line are relative to /root/reference):
 //   src/kitti_motion_compensation/motion_compensation.cpp:9-28      MotionCompensatePoint / MotionCompensateFrame
@@ -33,7 +36,7 @@
 // Eigen in the last ulp (effect on deskewed coordinates << 1e-12 m).
 //
 // The redundant per-point work of the reference (Log, SVD and three general inverses per point) is KEPT on
-// purpose: this file is also the timed "reference CPU path" of bench.py.
+// purpose: this file is the timed "reference CPU path" of bench.py whenever oracle/_ref has not been built.
 
 #include <algorithm>
 #include <atomic>

@@ -24,6 +24,7 @@
 #include "kmc_kernels.cuh"
 #include "kmc_point_math.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -218,13 +219,13 @@ __device__ __forceinline__ float4 ProjectPoint(float4 p, const kmc_b200_camera_p
   return make_float4(pu * inv, pv * inv, zr, culled ? -1.0f : zr * K.color_gain);
 }
 
-template <bool DESKEW, bool WRITE_CLOUD, int MODE, bool VEC2>
-__global__ void __launch_bounds__(kBlockThreads)
+template <bool DESKEW, bool WRITE_CLOUD, int MODE, bool VEC2, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
     ProjectFrameKernel(const float4* __restrict__ in, float4* __restrict__ cloud_out, float4* __restrict__ pix_out, int64_t n,
                        const __grid_constant__ kmc_b200_frame_params P, const __grid_constant__ kmc_b200_camera_params K) {
   if constexpr (!VEC2) {  // buffers only 16-byte aligned: one point per 128-bit access
-    int64_t const stride1 = static_cast<int64_t>(gridDim.x) * kBlockThreads;
-    for (int64_t j = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; j < n; j += stride1) {
+    int64_t const stride1 = static_cast<int64_t>(gridDim.x) * BLOCK;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * BLOCK + threadIdx.x; j < n; j += stride1) {
       float4 p = LoadPoint<0>(in + j);
       if constexpr (DESKEW) {
         p = DeskewPoint<MODE>(p, P);
@@ -234,8 +235,8 @@ __global__ void __launch_bounds__(kBlockThreads)
     }
     return;
   }
-  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads * 2;
-  int64_t i = (static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x) * 2;
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * BLOCK * 2;
+  int64_t i = (static_cast<int64_t>(blockIdx.x) * BLOCK + threadIdx.x) * 2;
   for (; i + 1 < n; i += stride) {  // two points per 256-bit access
     Point2 v = LoadPoint2<0>(in + i);
     if constexpr (DESKEW) {
@@ -267,12 +268,41 @@ struct PixelPlanes4 {
   float4* plane[4];
 };
 
-template <bool DESKEW, bool WRITE_CLOUD, int MODE>
-__global__ void __launch_bounds__(kBlockThreads)
+template <bool DESKEW, bool WRITE_CLOUD, int MODE, bool VEC2, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
     ProjectFrame4Kernel(const float4* __restrict__ in, float4* __restrict__ cloud_out, PixelPlanes4 const pix_out, int64_t n,
                         const __grid_constant__ kmc_b200_frame_params P, const __grid_constant__ Cameras4 K) {
-  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; i < n; i += stride) {
+  if constexpr (!VEC2) {  // buffers only 16-byte aligned: one point per 128-bit access
+    int64_t const stride1 = static_cast<int64_t>(gridDim.x) * BLOCK;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * BLOCK + threadIdx.x; i < n; i += stride1) {
+      float4 p = LoadPoint<0>(in + i);
+      if constexpr (DESKEW) {
+        p = DeskewPoint<MODE>(p, P);
+        if constexpr (WRITE_CLOUD) StorePoint<0>(cloud_out + i, p);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) StorePoint<0>(pix_out.plane[c] + i, ProjectPoint(p, K.cam[c]));
+    }
+    return;
+  }
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * BLOCK * 2;
+  int64_t i = (static_cast<int64_t>(blockIdx.x) * BLOCK + threadIdx.x) * 2;
+  for (; i + 1 < n; i += stride) {  // two points per 256-bit access
+    Point2 v = LoadPoint2<0>(in + i);
+    if constexpr (DESKEW) {
+      v.a = DeskewPoint<MODE>(v.a, P);
+      v.b = DeskewPoint<MODE>(v.b, P);
+      if constexpr (WRITE_CLOUD) StorePoint2<0>(cloud_out + i, v);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      Point2 r;
+      r.a = ProjectPoint(v.a, K.cam[c]);
+      r.b = ProjectPoint(v.b, K.cam[c]);
+      StorePoint2<0>(pix_out.plane[c] + i, r);
+    }
+  }
+  if (i < n) {  // odd tail
     float4 p = LoadPoint<0>(in + i);
     if constexpr (DESKEW) {
       p = DeskewPoint<MODE>(p, P);
@@ -563,22 +593,83 @@ cudaError_t LaunchDeskewBatch(const float* in, float* out, const int64_t* offset
 }
 
 namespace {
+// Launch shape of the projection kernels: threads per CTA, resident CTAs per SM (persistent grid) and 128- vs 256-bit
+// accesses; KMC_B200_TUNE="pblock=128,pctas=9,pvec=2" overrides the defaults for tools/sweep_projection.py.
+// Defaults from the B200 sweep (profiles/r01_sweep_projection.log, 100 M points): the best number of resident threads per
+// SM falls as the stores per thread rise, i.e. what is held constant is the memory traffic in flight per SM —
+//   1 load + 1 store  (project only)            128 x 8   6 570 GB/s   (5 x 256: 6 017)
+//   1 load + 1 store  (deskew + project)        256 x 5   6 377        (more arithmetic per point, wants more warps)
+//   1 load + 2 stores (deskew + project + cloud) 128 x 6   6 391        (5 x 256: 5 825)
+//   1 load + 4 stores (four cameras)            128 x 5   6 270        (5 x 256, 128-bit: 5 354)
+//   1 load + 5 stores (four cameras + cloud)    128 x 5   5 997        (5 x 256, 128-bit: 5 296)
+struct ProjectShape {
+  int block = 128;
+  int ctas_per_sm = 8;
+  int vec = 2;
+};
+
+ProjectShape PickProjectShape(bool aligned32, int stores_per_thread, bool deskew) {
+  ProjectShape shape;
+  shape.ctas_per_sm = stores_per_thread >= 4 ? 5 : stores_per_thread == 2 ? 6 : deskew ? 5 : 8;
+  if (deskew && stores_per_thread == 1) shape.block = 256;
+  if (const char* env = std::getenv("KMC_B200_TUNE")) {
+    auto find = [&](const char* key, int* out) {
+      size_t const len = std::strlen(key);
+      for (const char* p = env; *p;) {
+        if (std::strncmp(p, key, len) == 0 && p[len] == '=') *out = std::atoi(p + len + 1);
+        while (*p && *p != ',') ++p;
+        if (*p == ',') ++p;
+      }
+    };
+    find("pblock", &shape.block);
+    find("pctas", &shape.ctas_per_sm);
+    find("pvec", &shape.vec);
+  }
+  if (shape.block != 128) shape.block = 256;
+  shape.ctas_per_sm = std::min(std::max(shape.ctas_per_sm, 1), 16);
+  if (!aligned32 || shape.vec != 2) shape.vec = 1;
+  return shape;
+}
+
+unsigned ProjectGrid(int64_t n, const ProjectShape& shape, int sm_count) {
+  int64_t const per_cta = static_cast<int64_t>(shape.block) * shape.vec;
+  int64_t const grid = (n + per_cta - 1) / per_cta;
+  return static_cast<unsigned>(std::min<int64_t>(grid, static_cast<int64_t>(sm_count) * shape.ctas_per_sm));
+}
+
 template <bool DESKEW, bool WRITE_CLOUD, int MODE>
 cudaError_t LaunchProjectT(const float* in, float* cloud_out, float* pix_out, int64_t n, const kmc_b200_frame_params& P,
                            const kmc_b200_camera_params& K, bool vec2, int sm_count, cudaStream_t stream) {
-  int64_t const per_cta = static_cast<int64_t>(kBlockThreads) * (vec2 ? 2 : 1);
-  int64_t grid = (n + per_cta - 1) / per_cta;
-  int64_t const cap = static_cast<int64_t>(sm_count) * 5;
-  if (grid > cap) grid = cap;
+  ProjectShape const shape = PickProjectShape(vec2, WRITE_CLOUD ? 2 : 1, DESKEW);
+  unsigned const grid = ProjectGrid(n, shape, sm_count);
   auto const* in4 = reinterpret_cast<const float4*>(in);
   auto* cloud4 = reinterpret_cast<float4*>(cloud_out);
   auto* pix4 = reinterpret_cast<float4*>(pix_out);
-  if (vec2)
-    ProjectFrameKernel<DESKEW, WRITE_CLOUD, MODE, true><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(in4, cloud4, pix4, n, P, K);
-  else
-    ProjectFrameKernel<DESKEW, WRITE_CLOUD, MODE, false><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(in4, cloud4, pix4, n, P, K);
+#define KMC_PROJECT_CALL(V, B) ProjectFrameKernel<DESKEW, WRITE_CLOUD, MODE, V, B><<<grid, B, 0, stream>>>(in4, cloud4, pix4, n, P, K)
+  if (shape.vec == 2) {
+    if (shape.block == 128) KMC_PROJECT_CALL(true, 128);
+    else KMC_PROJECT_CALL(true, 256);
+  } else {
+    if (shape.block == 128) KMC_PROJECT_CALL(false, 128);
+    else KMC_PROJECT_CALL(false, 256);
+  }
+#undef KMC_PROJECT_CALL
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
+}
+
+template <bool DESKEW, bool WRITE_CLOUD, int MODE>
+void LaunchProject4T(const float4* in4, float4* cloud4, const PixelPlanes4& planes, int64_t n, const kmc_b200_frame_params& P,
+                     const Cameras4& K, const ProjectShape& shape, unsigned grid, cudaStream_t stream) {
+#define KMC_PROJECT4_CALL(V, B) ProjectFrame4Kernel<DESKEW, WRITE_CLOUD, MODE, V, B><<<grid, B, 0, stream>>>(in4, cloud4, planes, n, P, K)
+  if (shape.vec == 2) {
+    if (shape.block == 128) KMC_PROJECT4_CALL(true, 128);
+    else KMC_PROJECT4_CALL(true, 256);
+  } else {
+    if (shape.block == 128) KMC_PROJECT4_CALL(false, 128);
+    else KMC_PROJECT4_CALL(false, 256);
+  }
+#undef KMC_PROJECT4_CALL
 }
 }  // namespace
 
@@ -603,25 +694,25 @@ cudaError_t LaunchProject4(const float* in, float* cloud_out, float* const pix_o
   if (n <= 0) return cudaSuccess;
   Cameras4 K;
   PixelPlanes4 planes;
+  bool aligned32 = (reinterpret_cast<uintptr_t>(in) % 32 == 0) && (!cloud_out || reinterpret_cast<uintptr_t>(cloud_out) % 32 == 0);
   for (int c = 0; c < 4; ++c) {
     K.cam[c] = cameras[c];
     planes.plane[c] = reinterpret_cast<float4*>(pix_out[c]);
+    aligned32 = aligned32 && (reinterpret_cast<uintptr_t>(pix_out[c]) % 32 == 0);
   }
-  int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
-  int64_t const cap = static_cast<int64_t>(sm_count) * 5;
-  if (grid > cap) grid = cap;
+  ProjectShape const shape = PickProjectShape(aligned32, cloud_out ? 5 : 4, params != nullptr);
+  unsigned const grid = ProjectGrid(n, shape, sm_count);
   auto const* in4 = reinterpret_cast<const float4*>(in);
   auto* cloud4 = reinterpret_cast<float4*>(cloud_out);
-  unsigned const g = static_cast<unsigned>(grid);
   kmc_b200_frame_params const none{};
   if (!params) {
-    ProjectFrame4Kernel<false, false, 0><<<g, kBlockThreads, 0, stream>>>(in4, nullptr, planes, n, none, K);
+    LaunchProject4T<false, false, 0>(in4, nullptr, planes, n, none, K, shape, grid, stream);
   } else if (mode == KMC_B200_TIME_FROM_AZIMUTH) {
-    if (cloud_out) ProjectFrame4Kernel<true, true, KMC_B200_TIME_FROM_AZIMUTH><<<g, kBlockThreads, 0, stream>>>(in4, cloud4, planes, n, *params, K);
-    else ProjectFrame4Kernel<true, false, KMC_B200_TIME_FROM_AZIMUTH><<<g, kBlockThreads, 0, stream>>>(in4, nullptr, planes, n, *params, K);
+    if (cloud_out) LaunchProject4T<true, true, KMC_B200_TIME_FROM_AZIMUTH>(in4, cloud4, planes, n, *params, K, shape, grid, stream);
+    else LaunchProject4T<true, false, KMC_B200_TIME_FROM_AZIMUTH>(in4, nullptr, planes, n, *params, K, shape, grid, stream);
   } else {
-    if (cloud_out) ProjectFrame4Kernel<true, true, KMC_B200_TIME_FROM_W><<<g, kBlockThreads, 0, stream>>>(in4, cloud4, planes, n, *params, K);
-    else ProjectFrame4Kernel<true, false, KMC_B200_TIME_FROM_W><<<g, kBlockThreads, 0, stream>>>(in4, nullptr, planes, n, *params, K);
+    if (cloud_out) LaunchProject4T<true, true, KMC_B200_TIME_FROM_W>(in4, cloud4, planes, n, *params, K, shape, grid, stream);
+    else LaunchProject4T<true, false, KMC_B200_TIME_FROM_W>(in4, nullptr, planes, n, *params, K, shape, grid, stream);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();

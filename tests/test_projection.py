@@ -170,3 +170,41 @@ def test_four_cameras_in_one_pass_equal_four_launches(capi, cuda):
         assert torch.equal(planes[c], singles[c]), f"camera {c} (fused)"
     with pytest.raises(capi.KmcError):  # two planes aliasing each other
         capi.deskew_project_frame4_device(d_in.data_ptr(), 0, [planes[0].data_ptr()] * 4, n, None, cams, 0, s)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 257, 100_001])
+def test_four_camera_kernel_ragged_and_unaligned(capi, cuda, n):
+    """The four-camera kernel's 256-bit path (with its odd tail) and its 128-bit path (buffers only 16-byte aligned) both
+    equal four single-camera launches bit for bit, with and without the fused deskew, and stay inside their buffers."""
+    torch = cuda
+    T, R_rect, P = calibration()
+    cams = [capi.camera_params_from_calibration(P[k], R_rect, T, 15.0) for k in ("00", "01", "02", "03")]
+    pts = helpers.real_scan()[:n]
+    T_start, T_end, t0, t1, t2 = helpers.config1_frame()
+    p = capi.frame_params_from_poses(T_start, T_end, t0, t2, t1)
+    s = torch.cuda.current_stream().cuda_stream
+    aligned = torch.from_numpy(pts).cuda()
+    shifted = torch.zeros((n + 2, 4), dtype=torch.float32, device="cuda")
+    shifted[1:n + 1] = aligned
+    for params in (None, p):
+        want = [torch.empty_like(aligned) for _ in range(4)]
+        src = aligned
+        if params is not None:
+            src = torch.empty_like(aligned)
+            capi.deskew_frame_device(aligned.data_ptr(), src.data_ptr(), n, params, 0, s)
+        for c in range(4):
+            capi.project_frame_device(src.data_ptr(), want[c].data_ptr(), n, cams[c], s)
+        for offset in (0, 1):  # 0: 32-byte aligned buffers (256-bit path), 1: shifted by one point (128-bit path)
+            planes = [torch.full((n + 2, 4), 7.0, dtype=torch.float32, device="cuda") for _ in range(4)]
+            cloud = torch.full((n + 2, 4), 7.0, dtype=torch.float32, device="cuda")
+            d_in = shifted[1:] if offset else aligned
+            capi.deskew_project_frame4_device(d_in.data_ptr(), cloud[offset:].data_ptr() if params is not None else 0,
+                                              [q[offset:].data_ptr() for q in planes], n, params, cams, 0, s)
+            torch.cuda.synchronize()
+            for c in range(4):
+                assert torch.equal(planes[c][offset:offset + n], want[c]), (n, offset, c)
+                assert float(planes[c][offset + n:].min()) == 7.0 and (offset == 0 or float(planes[c][0].min()) == 7.0)
+            if params is not None:
+                assert torch.equal(cloud[offset:offset + n], src)
+                assert float(cloud[offset + n:].min()) == 7.0

@@ -255,7 +255,8 @@ KMC_B200_API int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_i
  * read -> H2D -> batched kernel -> D2H -> write with io_threads readers and writers (<= 0: min(16, host threads)).
  * This is the loop body of MotionCompensateRun (handlers.cpp:55-64: LoadSingleFrame + MotionCompensateFrame +
  * WritePointcloud per frame) for n_files frames at once; params[f] belongs to paths_in[f].  points_out (optional)
- * receives the number of points of every file.  A file larger than the handle's capacity is KMC_B200_ERR_CAPACITY. */
+ * receives the number of points of every file.  A file larger than a staging slot is streamed through the slots in chunks on
+ * its own (the pipeline drains around it). */
 KMC_B200_API int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* const* paths_in,
                                            const char* const* paths_out, const kmc_b200_frame_params* params, int time_mode,
                                            int32_t io_threads, int64_t* points_out);

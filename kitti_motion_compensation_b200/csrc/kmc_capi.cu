@@ -916,8 +916,6 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
     if (st.st_size % 16 != 0)
       return Fail(KMC_B200_ERR_IO, std::string("KITTI pointcloud binary file is not a whole number of xyzi points: ") + paths_in[f]);
     int64_t const n = static_cast<int64_t>(st.st_size / 16);
-    if (n > h->capacity)
-      return Fail(KMC_B200_ERR_CAPACITY, std::string("scan larger than the handle's capacity (create the handle with more points): ") + paths_in[f]);
     offsets[static_cast<size_t>(f) + 1] = offsets[static_cast<size_t>(f)] + n;
     if (points_out) points_out[f] = n;
   }
@@ -998,6 +996,28 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
     Group const grp = groups[g];
     int64_t const base = offsets[static_cast<size_t>(grp.first_file)];
     int64_t const count = offsets[static_cast<size_t>(grp.end_file)] - base;
+    if (count > h->capacity) {
+      // One file larger than a staging slot (a group of its own): let the pipeline drain, then stream the file through all
+      // three slots in capacity-sized chunks, as kmc_b200_deskew_batch_host does for an array.
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        slot_free[slot] = true;
+        cv.wait(lk, [&] { return submitted.empty() && std::all_of(slot_free, slot_free + kSlots, [](bool b) { return b; }); });
+        if (retire_status != KMC_B200_OK) break;
+      }
+      size_t const f = static_cast<size_t>(grp.first_file);
+      std::vector<float> big_in(static_cast<size_t>(count) * 4), big_out(static_cast<size_t>(count) * 4);
+      status = ReadWholeFile(paths_in[f], big_in.data(), static_cast<size_t>(count) * 16);
+      if (status == KMC_B200_OK)
+        status = StreamThroughDevice(h, big_in.data(), big_out.data(), count, [&](int s, int64_t first, int64_t chunk) -> int {
+          auto const cfg = kmc_b200::dev::PickConfig(chunk, true, false, h->sm_count);
+          KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[s], h->d_out[s], h->d_offsets, h->d_params, n_files, chunk, base + first,
+                                                        n_total, mode, cfg, h->sm_count, h->stream[s]));
+          return KMC_B200_OK;
+        });
+      if (status == KMC_B200_OK) status = WriteWholeFile(paths_out[f], big_out.data(), static_cast<size_t>(count) * 16);
+      continue;
+    }
     status = ParallelFor(grp.end_file - grp.first_file, io_threads, [&](int64_t k) -> int {
       size_t const f = static_cast<size_t>(grp.first_file + k);
       return ReadWholeFile(paths_in[f], h->h_in[slot] + 4 * (offsets[f] - base), static_cast<size_t>(offsets[f + 1] - offsets[f]) * 16);

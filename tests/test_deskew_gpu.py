@@ -724,10 +724,16 @@ def test_bin_files_pipeline_matches_per_frame_calls(capi, oracle, cuda, tmp_path
         with pytest.raises(capi.KmcError) as e:
             h.deskew_bin_files([str(tmp_path / "odd.bin")], [paths_out[0]], params[:1])
         assert e.value.status == capi.ERR_IO
-        helpers.synthetic_scan(16_001, 64, 1).tofile(str(tmp_path / "big.bin"))
-        with pytest.raises(capi.KmcError) as e:
-            h.deskew_bin_files([str(tmp_path / "big.bin")], [paths_out[0]], params[:1])
-        assert e.value.status == capi.ERR_CAPACITY
+        # a file larger than a staging slot is streamed through the slots in chunks, between ordinary groups
+        big = helpers.synthetic_scan(16_000 * 3 + 1234, 64, 1)
+        big.tofile(str(tmp_path / "big.bin"))
+        mixed_in = [paths_in[0], str(tmp_path / "big.bin"), paths_in[3], str(tmp_path / "big.bin"), paths_in[5]]
+        mixed_out = [str(tmp_path / f"mixed_{k}.bin") for k in range(5)]
+        mixed_params = params[[0, 1, 3, 2, 5]]
+        assert h.deskew_bin_files(mixed_in, mixed_out, mixed_params, io_threads=3).tolist() == [sizes[0], len(big), sizes[3], len(big), sizes[5]]
+        for k, (src, prm) in enumerate(zip([scans[0], big, scans[3], big, scans[5]], mixed_params)):
+            want = run_frame(cuda, capi, src, capi.FrameParams.from_buffer_copy(prm.tobytes()))
+            assert np.array_equal(helpers.read_bin(mixed_out[k]), want), f"mixed file {k}"
         with pytest.raises(capi.KmcError) as e:
             h.deskew_bin_files(paths_in[:1], [str(tmp_path / "no_such_dir" / "x.bin")], params[:1])
         assert e.value.status == capi.ERR_IO

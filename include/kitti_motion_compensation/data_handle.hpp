@@ -75,6 +75,29 @@ class DataHandle {
     return n;
   }
 
+  // Many .bin files as one overlapped read -> H2D -> kernel -> D2H -> write pipeline (params[k] belongs to paths_in[k]);
+  // returns the points per file.  Give the handle a capacity of several scans so that a staging slot holds a group.
+  std::vector<std::int64_t> DeskewBinFiles(std::vector<std::string> const& paths_in, std::vector<std::string> const& paths_out,
+                                           std::vector<kmc_b200_frame_params> const& params, int io_threads = 0) {
+    if (paths_in.size() != params.size() || paths_out.size() != params.size())
+      throw std::invalid_argument("DeskewBinFiles: paths_in, paths_out and params must have the same length");
+    std::vector<const char*> in, out;
+    for (auto const& p : paths_in) in.push_back(p.c_str());
+    for (auto const& p : paths_out) out.push_back(p.c_str());
+    std::vector<std::int64_t> points(params.size(), 0);
+    ThrowOnError(kmc_b200_deskew_bin_files(handle_, static_cast<std::int32_t>(params.size()), in.data(), out.data(), params.data(),
+                                           KMC_B200_TIME_FROM_AZIMUTH, io_threads, points.data()),
+                 "kmc_b200_deskew_bin_files");
+    return points;
+  }
+
+  // A whole KITTI raw run folder (the reference's MotionCompensateRun, handlers.cpp:41-65) with this handle's buffers.
+  kmc_b200_run_stats MotionCompensateRun(std::string const& run_folder, int io_threads = 0) {
+    kmc_b200_run_stats stats{};
+    ThrowOnError(kmc_b200_motion_compensate_run(handle_, run_folder.c_str(), io_threads, &stats), "kmc_b200_motion_compensate_run");
+    return stats;
+  }
+
  private:
   kmc_b200_handle* handle_ = nullptr;
 };

@@ -3,9 +3,11 @@
 // round trip of test/test_data_io.cpp:115-149, and a whole MotionCompensateRun on a generated run folder —
 // all through this repository's drop-in headers, i.e. through the CUDA kernels.  argv[2] = path of the real scan.
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <filesystem>
 #include <fstream>
+#include <iterator>
 #include <memory>
 #include <random>
 
@@ -260,6 +262,41 @@ TEST(DataHandleTest, FloatPathMatchesFrameApi) {
   ASSERT_FLOAT_EQ(out[3], 0.7);
   ASSERT_FLOAT_EQ(out[11], 0.9);
   ASSERT_THROW(kmc::b200::FrameParamsFromPoses(Ts.data(), Te.data(), 0.1, 0.2, 0.5), std::runtime_error);
+}
+
+TEST(DataHandleTest, BinFilesPipelineEqualsPerFileCalls) {
+  Frame const frame{MakeMotionCompensationTestFrame()};
+  auto const Ts{frame.T_start.matrix()};
+  auto const Te{frame.T_end.matrix()};
+  fs::path const dir{fs::temp_directory_path() / "kmc_b200_test_bin_files"};
+  fs::remove_all(dir);
+  fs::create_directories(dir);
+  std::vector<std::string> in, out_many, out_single;
+  std::vector<kmc_b200_frame_params> params;
+  for (int k = 0; k < 7; ++k) {
+    in.push_back((dir / ("in" + std::to_string(k) + ".bin")).string());
+    out_many.push_back((dir / ("many" + std::to_string(k) + ".bin")).string());
+    out_single.push_back((dir / ("single" + std::to_string(k) + ".bin")).string());
+    std::ofstream bin(in.back(), std::ios::binary);
+    for (int i = 0; i < 100 * k; ++i) {  // file 0 is empty
+      float const p[4] = {5.f * std::cos(0.05f * i), 5.f * std::sin(0.05f * i), 0.01f * k, 0.001f * i};
+      bin.write(reinterpret_cast<const char*>(p), sizeof(p));
+    }
+    params.push_back(kmc::b200::FrameParamsFromPoses(Ts.data(), Te.data(), 0.1, 0.2, 0.1 + 0.015 * k));
+  }
+  kmc::b200::DataHandle handle(0, 700);  // two or three of these files per staging slot
+  std::vector<std::int64_t> const points{handle.DeskewBinFiles(in, out_many, params, 2)};
+  for (int k = 0; k < 7; ++k) {
+    ASSERT_EQ(points[static_cast<size_t>(k)], std::int64_t{100} * k);
+    ASSERT_EQ(handle.DeskewBinFile(in[static_cast<size_t>(k)], out_single[static_cast<size_t>(k)], params[static_cast<size_t>(k)]), std::int64_t{100} * k);
+    std::ifstream a(out_many[static_cast<size_t>(k)], std::ios::binary), b(out_single[static_cast<size_t>(k)], std::ios::binary);
+    std::string const sa((std::istreambuf_iterator<char>(a)), std::istreambuf_iterator<char>());
+    std::string const sb((std::istreambuf_iterator<char>(b)), std::istreambuf_iterator<char>());
+    ASSERT_EQ(sa.size(), static_cast<size_t>(1600 * k));
+    ASSERT_TRUE(sa == sb);
+  }
+  ASSERT_THROW(handle.DeskewBinFiles({(dir / "missing.bin").string()}, {out_many[0]}, {params[0]}), std::runtime_error);
+  fs::remove_all(dir);
 }
 
 // ---- camera_model.cpp:5-95 without the drawing: the draw list of the real scan on camera 02 ------------------------------

@@ -346,14 +346,32 @@ __global__ void __launch_bounds__(kBlockThreads)
 // ---------------------------------------------------------------------------------------------------------------
 // GetPseudoTimeStamps (timestamp_mocking.cpp:56-63) in double, for callers that want the stamps themselves.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlockThreads)
+constexpr int kStampBlockThreads = 128;
+
+template <bool VEC2>
+__global__ void __launch_bounds__(kStampBlockThreads)
     PseudoTimeStampsKernel(const float4* __restrict__ in, double* __restrict__ stamps, int64_t n, double start, double duration) {
-  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; i < n; i += stride) {
-    float4 const p = LoadPoint<1>(in + i);
-    double const frac = (3.14159265358979323846 - atan2(static_cast<double>(p.y), static_cast<double>(p.x))) /
-                        (2.0 * 3.14159265358979323846);
-    stamps[i] = start + frac * duration;
+  if constexpr (!VEC2) {
+    int64_t const stride1 = static_cast<int64_t>(gridDim.x) * kStampBlockThreads;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kStampBlockThreads + threadIdx.x; i < n; i += stride1) {
+      float4 const p = LoadPoint<0>(in + i);
+      stamps[i] = fma(FractionOfScanF64(p.y, p.x), duration, start);
+    }
+    return;
+  }
+  // two points per 256-bit load, two stamps per 128-bit store
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * kStampBlockThreads * 2;
+  int64_t i = (static_cast<int64_t>(blockIdx.x) * kStampBlockThreads + threadIdx.x) * 2;
+  for (; i + 1 < n; i += stride) {
+    Point2 const v = LoadPoint2<0>(in + i);
+    double2 out;
+    out.x = fma(FractionOfScanF64(v.a.y, v.a.x), duration, start);
+    out.y = fma(FractionOfScanF64(v.b.y, v.b.x), duration, start);
+    *reinterpret_cast<double2*>(stamps + i) = out;
+  }
+  if (i < n) {
+    float4 const p = LoadPoint<0>(in + i);
+    stamps[i] = fma(FractionOfScanF64(p.y, p.x), duration, start);
   }
 }
 
@@ -362,8 +380,7 @@ __global__ void __launch_bounds__(kBlockThreads)
                              double start, double duration) {
   int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; i < n; i += stride) {
-    double const frac = (3.14159265358979323846 - atan2(__ldg(y + i), __ldg(x + i))) / (2.0 * 3.14159265358979323846);
-    stamps[i] = start + frac * duration;
+    stamps[i] = fma(0.5 - Atan2TurnsF64(__ldg(y + i), __ldg(x + i)), duration, start);
   }
 }
 
@@ -721,11 +738,14 @@ cudaError_t LaunchProject4(const float* in, float* cloud_out, float* const pix_o
 cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,
                                    cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
-  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  bool const vec2 = (reinterpret_cast<uintptr_t>(in) % 32 == 0) && (reinterpret_cast<uintptr_t>(stamps) % 16 == 0);
+  int64_t const per_cta = static_cast<int64_t>(kStampBlockThreads) * (vec2 ? 2 : 1);
+  int64_t grid = (n + per_cta - 1) / per_cta;
+  int64_t const cap = static_cast<int64_t>(sm_count) * 9;  // 1152 resident threads per SM, as the deskew kernel
   if (grid > cap) grid = cap;
-  PseudoTimeStampsKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(reinterpret_cast<const float4*>(in), stamps, n,
-                                                                                    start, end - start);
+  auto const* in4 = reinterpret_cast<const float4*>(in);
+  if (vec2) PseudoTimeStampsKernel<true><<<static_cast<unsigned>(grid), kStampBlockThreads, 0, stream>>>(in4, stamps, n, start, end - start);
+  else PseudoTimeStampsKernel<false><<<static_cast<unsigned>(grid), kStampBlockThreads, 0, stream>>>(in4, stamps, n, start, end - start);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

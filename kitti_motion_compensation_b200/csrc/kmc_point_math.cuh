@@ -41,6 +41,80 @@ __device__ __forceinline__ float Atan2Turns(float y, float x) {
   return copysignf(q, y);
 }
 
+// The same in double, for the GetPseudoTimeStamps entry points (timestamp_mocking.cpp:46-63), whose stamps are doubles of
+// magnitude ~4.7e4 s: libdevice's atan2 costs ~120 FP64 instructions per point and made those kernels FP64-bound
+// (3.5 TB/s); this costs ~30.  atan(r)/(2 pi r) on [0,1] as a degree-12 interpolant in r^2 at Chebyshev nodes:
+// |err| < 1e-12 turns evaluated in double, i.e. < 1e-13 s on a 0.1 s scan (1 ulp of the stamps is 7e-12 s).
+// The quotient min/max comes from the fp32 reciprocal refined by one Newton step in double (relative error ~1e-14).
+__device__ __forceinline__ double Atan2TurnsF64(double y, double x) {
+  double const ax = fabs(x), ay = fabs(y);
+  double const mx = fmax(ax, ay), mn = fmin(ax, ay);
+  double r;
+  if (mx > 1e-30 && mx < 1e30) {
+    float seed;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(static_cast<float>(mx)));
+    double const x0 = static_cast<double>(seed);
+    r = mn * (x0 * fma(-mx, x0, 2.0));
+  } else {
+    r = (mx > 0.0) ? mn / mx : 0.0;  // atan2(+-0, +-0): no 0/0; values outside the fp32 range take the exact quotient
+  }
+  double const t = r * r;
+  double p = 6.67221862187784099e-05;
+  p = fma(p, t, -5.08567722343806756e-04);
+  p = fma(p, t, 1.81876432393576174e-03);
+  p = fma(p, t, -4.13898280986435812e-03);
+  p = fma(p, t, 6.94657045892680715e-03);
+  p = fma(p, t, -9.58462323410399705e-03);
+  p = fma(p, t, 1.19290805724528125e-02);
+  p = fma(p, t, -1.44022158368946745e-02);
+  p = fma(p, t, 1.76746446101705770e-02);
+  p = fma(p, t, -2.27356426872162426e-02);
+  p = fma(p, t, 3.18309541393976964e-02);
+  p = fma(p, t, -5.30516470898420370e-02);
+  p = fma(p, t, 1.59154943090102946e-01);
+  double q = r * p;
+  q = (ay > ax) ? (0.25 - q) : q;
+  q = (__double2hiint(x) < 0) ? (0.5 - q) : q;  // sign BIT of x
+  return copysign(q, y);
+}
+
+// FractionOfScanCompleted (timestamp_mocking.cpp:46) in double for a point whose coordinates ARE floats (the .bin
+// layout): the octant logic — |x| vs |y|, the sign bits — is exact in fp32, so only the quotient, the polynomial and the
+// final fold run in double.  The two folds of Atan2TurnsF64 collapse into frac = A + B q with A, B small exact constants
+// picked in fp32, which keeps q = 0 (a point on an axis) exact: frac = 1 for y = -0, x < 0; 0 for y = +0, x < 0; 0.5 for
+// x = y = 0.  ~45 instructions per point instead of ~150.  Domain: |x|, |y| < 1e30 (larger values give r = 0).
+__device__ __forceinline__ double FractionOfScanF64(float y, float x) {
+  float const ax = fabsf(x), ay = fabsf(y);
+  float const mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float seed;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(mx));
+  seed = (mx > 1e-30f) ? seed : 0.0f;  // atan2(+-0, +-0): r = 0, no 0 * inf
+  double const x0 = static_cast<double>(seed);
+  double const dmx = static_cast<double>(mx);
+  double const r = static_cast<double>(mn) * (x0 * fma(-dmx, x0, 2.0));  // one Newton step: relative error ~1e-14
+  double const t = r * r;
+  double p = 6.67221862187784099e-05;
+  p = fma(p, t, -5.08567722343806756e-04);
+  p = fma(p, t, 1.81876432393576174e-03);
+  p = fma(p, t, -4.13898280986435812e-03);
+  p = fma(p, t, 6.94657045892680715e-03);
+  p = fma(p, t, -9.58462323410399705e-03);
+  p = fma(p, t, 1.19290805724528125e-02);
+  p = fma(p, t, -1.44022158368946745e-02);
+  p = fma(p, t, 1.76746446101705770e-02);
+  p = fma(p, t, -2.27356426872162426e-02);
+  p = fma(p, t, 3.18309541393976964e-02);
+  p = fma(p, t, -5.30516470898420370e-02);
+  p = fma(p, t, 1.59154943090102946e-01);
+  double const q = r * p;  // atan(min/max) / 2 pi in [0, 1/8]
+  // turns = sy (c + m q);  frac = 0.5 - turns = (0.5 - sy c) + (-sy m) q
+  bool const steep = ay > ax, back = (__float_as_uint(x) >> 31) != 0;
+  float const c = steep ? 0.25f : (back ? 0.5f : 0.0f);
+  float const m = (steep != back) ? -1.0f : 1.0f;
+  float const sy = (__float_as_uint(y) >> 31) ? -1.0f : 1.0f;
+  return fma(static_cast<double>(-sy * m), q, static_cast<double>(0.5f - sy * c));
+}
+
 // S = sin(s th)/th and C = (1 - cos(s th))/th^2 for x2 = (s th)^2 <= 1, as s*P(x2) and s^2*Q(x2).
 __device__ __forceinline__ void SeriesSC(float s, float s2, float x2, float& S, float& C) {
   float ps = 2.755731922e-06f;  // 1/9!

@@ -12,7 +12,7 @@ INC       := include
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --shared -Xcompiler -fPIC,-fvisibility=hidden -cudart static
 CXXFLAGS  := -std=c++17 -O2 -fPIC -Wall -Wextra
 
-KERNEL_SRC := $(CSRC)/kmc_kernels.cu $(CSRC)/kmc_kernels_bulk.cu $(CSRC)/kmc_capi.cu $(CSRC)/kmc_host_math.cpp $(CSRC)/kmc_run.cpp
+KERNEL_SRC := $(CSRC)/kmc_kernels.cu $(CSRC)/kmc_kernels_bulk.cu $(CSRC)/kmc_capi.cu $(CSRC)/kmc_pipeline.cu $(CSRC)/kmc_host_math.cpp $(CSRC)/kmc_run.cpp
 KERNEL_HDR := $(CSRC)/kmc_kernels.cuh $(CSRC)/kmc_point_math.cuh $(CSRC)/kmc_host_math.hpp $(CSRC)/kmc_internal.hpp $(INC)/kmc_b200.h
 MIRROR_HDR := $(wildcard $(INC)/kitti_motion_compensation/*.hpp)
 

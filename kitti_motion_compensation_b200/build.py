@@ -17,7 +17,7 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libkmc_b200.so")
 DROPIN_LIB_PATH = os.path.join(LIB_DIR, "libkitti_motion_compensation_lib.so")
 
-SOURCES = ["kmc_kernels.cu", "kmc_kernels_bulk.cu", "kmc_capi.cu", "kmc_host_math.cpp", "kmc_run.cpp"]
+SOURCES = ["kmc_kernels.cu", "kmc_kernels_bulk.cu", "kmc_capi.cu", "kmc_pipeline.cu", "kmc_host_math.cpp", "kmc_run.cpp"]
 HEADERS = ["kmc_kernels.cuh", "kmc_point_math.cuh", "kmc_host_math.hpp", "kmc_internal.hpp", os.path.join(REPO_DIR, "include", "kmc_b200.h")]
 
 NVCC_FLAGS = [

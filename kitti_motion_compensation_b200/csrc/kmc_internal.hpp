@@ -1,11 +1,84 @@
-// kmc_internal.hpp — the few symbols the translation units of libkmc_b200.so share that are not part of the C ABI.
+// kmc_internal.hpp — what the translation units of libkmc_b200.so share that is not part of the C ABI: error
+// recording, CUDA status plumbing, device selection, NVTX ranges.  Nothing here is visible outside the library.
 #pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
 
 #include <string>
 
+#include "kmc_b200.h"
+
+// NVTX ranges around the host entry points (visible in Nsight Systems / Compute timelines); header-only, no cost when
+// no tool is attached.
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define KMC_HAVE_NVTX 1
+#else
+#define KMC_HAVE_NVTX 0
+#endif
+
 namespace kmc_b200::internal {
 
-// Records `what` as the calling thread's kmc_b200_last_error() text and returns `status`.
+// The calling thread's kmc_b200_last_error() text.
+std::string& LastError();
+
+// Records `what` as the calling thread's last error and returns `status`.
 int SetError(int status, const std::string& what);
 
+// Records the CUDA error (name + text, prefixed by `where`) and maps it to KMC_B200_ERR_NO_DEVICE / KMC_B200_ERR_CUDA.
+int FailCuda(cudaError_t e, const char* where);
+
+constexpr int kMaxDevices = 64;  // device ordinals the per-device tables cover
+
+// Multiprocessor count of `device`, cached.
+int SmCount(int device, int* out);
+
+inline bool ValidMode(int mode) { return mode == KMC_B200_TIME_FROM_AZIMUTH || mode == KMC_B200_TIME_FROM_W; }
+inline bool Aligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+struct TraceRange {
+  explicit TraceRange(const char* name) {
+#if KMC_HAVE_NVTX
+    nvtxRangePushA(name);
+#else
+    (void)name;
+#endif
+  }
+  ~TraceRange() {
+#if KMC_HAVE_NVTX
+    nvtxRangePop();
+#endif
+  }
+  TraceRange(TraceRange const&) = delete;
+  TraceRange& operator=(TraceRange const&) = delete;
+};
+
+// Makes `device` current for the scope and restores the caller's device afterwards (handles may live on any device).
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&previous_) != cudaSuccess) previous_ = -1;
+    status_ = (previous_ == device) ? cudaSuccess : cudaSetDevice(device);
+    changed_ = (status_ == cudaSuccess && previous_ != device);
+  }
+  ~DeviceGuard() {
+    if (changed_ && previous_ >= 0) cudaSetDevice(previous_);
+  }
+  DeviceGuard(DeviceGuard const&) = delete;
+  DeviceGuard& operator=(DeviceGuard const&) = delete;
+  cudaError_t status() const { return status_; }
+
+ private:
+  int previous_ = -1;
+  bool changed_ = false;
+  cudaError_t status_ = cudaSuccess;
+};
+
 }  // namespace kmc_b200::internal
+
+#define KMC_CUDA_TRY(expr)                                                      \
+  do {                                                                          \
+    cudaError_t const e_ = (expr);                                              \
+    if (e_ != cudaSuccess) return ::kmc_b200::internal::FailCuda(e_, #expr);    \
+  } while (0)

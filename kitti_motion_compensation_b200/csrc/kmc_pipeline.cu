@@ -1,0 +1,706 @@
+// kmc_pipeline.cu — the C ABI declared in include/kmc_b200.h, part 2: the handle (device, streams, pinned + device
+// staging slots) and everything that moves data through it — host-buffer entry points (three-slot H2D / kernel / D2H
+// pipeline), multi-GPU frame sharding, and the KITTI .bin file pipelines (overlapped pread / copies / kernel / pwrite).
+// Every compute entry point ends in a kernel launch from kmc_kernels.cu or an error status; there is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kmc_b200.h"
+#include "kmc_internal.hpp"
+#include "kmc_kernels.cuh"
+
+namespace {
+
+using kmc_b200::internal::Aligned;
+using kmc_b200::internal::DeviceGuard;
+using kmc_b200::internal::FailCuda;
+using kmc_b200::internal::kMaxDevices;
+using kmc_b200::internal::SmCount;
+using kmc_b200::internal::TraceRange;
+using kmc_b200::internal::ValidMode;
+
+int Fail(int status, const std::string& what) { return kmc_b200::internal::SetError(status, what); }
+using kmc_b200::internal::LastError;
+
+bool IsPinnedHost(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();  // clear
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// =============================================================================================================
+// handle
+// =============================================================================================================
+struct kmc_b200_handle {
+  static constexpr int kSlots = 3;
+  int device = -1;
+  int sm_count = 0;
+  int64_t capacity = 0;  // points per staging slot
+  cudaStream_t stream[kSlots] = {};
+  cudaEvent_t done[kSlots] = {};
+  float* d_in[kSlots] = {};
+  float* d_out[kSlots] = {};
+  float* h_in[kSlots] = {};   // pinned
+  float* h_out[kSlots] = {};  // pinned
+  // device copies of the batch tables
+  int64_t* d_offsets = nullptr;
+  kmc_b200_frame_params* d_params = nullptr;
+  int64_t table_capacity = 0;  // frames
+  // scratch of the double-precision (reference layout) entry points, grown on demand and kept
+  double* d_f64 = nullptr;
+  size_t d_f64_bytes = 0;
+  std::mutex mu;
+};
+
+namespace {
+
+void FreeHandle(kmc_b200_handle* h) {
+  if (!h) return;
+  DeviceGuard const guard(h->device >= 0 ? h->device : 0);
+  for (int s = 0; s < kmc_b200_handle::kSlots; ++s) {
+    if (h->d_in[s]) cudaFree(h->d_in[s]);
+    if (h->d_out[s]) cudaFree(h->d_out[s]);
+    if (h->h_in[s]) cudaFreeHost(h->h_in[s]);
+    if (h->h_out[s]) cudaFreeHost(h->h_out[s]);
+    if (h->done[s]) cudaEventDestroy(h->done[s]);
+    if (h->stream[s]) cudaStreamDestroy(h->stream[s]);
+  }
+  if (h->d_offsets) cudaFree(h->d_offsets);
+  if (h->d_params) cudaFree(h->d_params);
+  if (h->d_f64) cudaFree(h->d_f64);
+  delete h;
+}
+
+int EnsureF64Scratch(kmc_b200_handle* h, size_t bytes) {
+  if (bytes <= h->d_f64_bytes) return KMC_B200_OK;
+  if (h->d_f64) cudaFree(h->d_f64);
+  h->d_f64 = nullptr;
+  h->d_f64_bytes = 0;
+  size_t const want = bytes + bytes / 4;  // head room: clouds of a run differ by a few percent in size
+  KMC_CUDA_TRY(cudaMalloc(&h->d_f64, want));
+  h->d_f64_bytes = want;
+  return KMC_B200_OK;
+}
+
+int EnsureTables(kmc_b200_handle* h, int64_t n_frames) {
+  if (n_frames <= h->table_capacity) return KMC_B200_OK;
+  if (h->d_offsets) cudaFree(h->d_offsets);
+  if (h->d_params) cudaFree(h->d_params);
+  h->d_offsets = nullptr;
+  h->d_params = nullptr;
+  h->table_capacity = 0;
+  int64_t const cap = std::max<int64_t>(n_frames, 1024);
+  KMC_CUDA_TRY(cudaMalloc(&h->d_offsets, static_cast<size_t>(cap + 1) * sizeof(int64_t)));
+  KMC_CUDA_TRY(cudaMalloc(&h->d_params, static_cast<size_t>(cap) * sizeof(kmc_b200_frame_params)));
+  h->table_capacity = cap;
+  return KMC_B200_OK;
+}
+
+// Streams a host array through the device in capacity-sized chunks: stage (if pageable) -> H2D -> kernel -> D2H ->
+// unstage, three slots deep so the copy engines and the SMs overlap.  `launch(slot, chunk_first_point, chunk_points)`
+// enqueues the kernel for a chunk on h->stream[slot].
+template <class Launch>
+int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch);
+
+// On any failure the slots' streams are drained before returning, so that no copy is still reading or writing the
+// caller's buffers after the call has reported an error.
+template <class Launch>
+int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
+  int const rc = StreamThroughDeviceImpl(h, in, out, n, launch);
+  if (rc != KMC_B200_OK) {
+    std::string const keep = LastError();
+    for (int s = 0; s < kmc_b200_handle::kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
+    cudaGetLastError();
+    LastError() = keep;
+  }
+  return rc;
+}
+
+// Pageable caller memory is staged through the handle's pinned slots.  One thread copies about 10-15 GB/s, a quarter of
+// what the PCIe link moves, so chunks of 8 MB and more are split over a few short-lived threads.
+void StagingCopy(void* dst, const void* src, size_t bytes) {
+  constexpr size_t kParallelFrom = size_t{8} << 20;
+  unsigned const hw = std::thread::hardware_concurrency();
+  if (bytes < kParallelFrom || hw < 4) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  size_t const parts = std::min<size_t>({size_t{8}, hw / 2, bytes / (size_t{2} << 20)});
+  size_t const each = ((bytes / parts) + 4095) & ~size_t{4095};
+  std::vector<std::thread> pool;
+  for (size_t k = 1; k < parts; ++k) {
+    size_t const begin = k * each;
+    if (begin >= bytes) break;
+    size_t const len = std::min(each, bytes - begin);
+    pool.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + begin, static_cast<const char*>(src) + begin, len); });
+  }
+  std::memcpy(dst, src, std::min(each, bytes));
+  for (auto& t : pool) t.join();
+}
+
+template <class Launch>
+int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
+  constexpr int kSlots = kmc_b200_handle::kSlots;
+  bool const in_pinned = IsPinnedHost(in);
+  bool const out_pinned = IsPinnedHost(out);
+  struct Pending {
+    int64_t first = 0, count = 0;
+    bool active = false;
+  } pending[kSlots];
+
+  auto retire = [&](int slot) -> int {
+    if (!pending[slot].active) return KMC_B200_OK;
+    KMC_CUDA_TRY(cudaEventSynchronize(h->done[slot]));
+    if (!out_pinned) StagingCopy(out + 4 * pending[slot].first, h->h_out[slot], static_cast<size_t>(pending[slot].count) * 16);
+    pending[slot].active = false;
+    return KMC_B200_OK;
+  };
+
+  int64_t chunk_index = 0;
+  for (int64_t first = 0; first < n; first += h->capacity, ++chunk_index) {
+    int const slot = static_cast<int>(chunk_index % kSlots);
+    int64_t const count = std::min(h->capacity, n - first);
+    size_t const bytes = static_cast<size_t>(count) * 16;
+    if (int rc = retire(slot)) return rc;
+    const float* src = in + 4 * first;
+    if (!in_pinned) {
+      StagingCopy(h->h_in[slot], src, bytes);
+      src = h->h_in[slot];
+    }
+    KMC_CUDA_TRY(cudaMemcpyAsync(h->d_in[slot], src, bytes, cudaMemcpyHostToDevice, h->stream[slot]));
+    if (int rc = launch(slot, first, count)) return rc;
+    float* dst = out_pinned ? out + 4 * first : h->h_out[slot];
+    KMC_CUDA_TRY(cudaMemcpyAsync(dst, h->d_out[slot], bytes, cudaMemcpyDeviceToHost, h->stream[slot]));
+    KMC_CUDA_TRY(cudaEventRecord(h->done[slot], h->stream[slot]));
+    pending[slot] = {first, count, true};
+  }
+  for (int k = 0; k < kSlots; ++k) {
+    int const slot = static_cast<int>((chunk_index + k) % kSlots);  // oldest first
+    if (int rc = retire(slot)) return rc;
+  }
+  return KMC_B200_OK;
+}
+
+int CheckOffsets(const int64_t* offsets, int32_t n_frames) {
+  if (offsets[0] != 0) return Fail(KMC_B200_ERR_BAD_SIZE, "frame_offsets[0] must be 0");
+  for (int32_t f = 0; f < n_frames; ++f)
+    if (offsets[f + 1] < offsets[f]) return Fail(KMC_B200_ERR_BAD_SIZE, "frame_offsets must be non-decreasing");
+  return KMC_B200_OK;
+}
+
+}  // namespace
+
+// =============================================================================================================
+// C ABI
+// =============================================================================================================
+extern "C" {
+
+// ---- handle ---------------------------------------------------------------------------------------------------------
+int kmc_b200_handle_create(int device, int64_t capacity_points, kmc_b200_handle** out) {
+  if (!out) return Fail(KMC_B200_ERR_NULL_POINTER, "handle_create: null output");
+  *out = nullptr;
+  if (capacity_points <= 0) return Fail(KMC_B200_ERR_BAD_SIZE, "handle_create: capacity must be positive");
+  int n_dev = kmc_b200_device_count();
+  if (n_dev < 0) return n_dev;
+  if (device < 0 || device >= n_dev) return Fail(KMC_B200_ERR_NO_DEVICE, "handle_create: no such device");
+  auto* h = new kmc_b200_handle;
+  h->device = device;
+  h->capacity = (capacity_points + 7) & ~int64_t{7};  // even point count per chunk keeps 256-bit accesses aligned
+  DeviceGuard const guard(device);
+  cudaError_t e = guard.status();
+  int rc = (e == cudaSuccess) ? SmCount(device, &h->sm_count) : FailCuda(e, "cudaSetDevice");
+  size_t const bytes = static_cast<size_t>(h->capacity) * 16;
+  for (int s = 0; s < kmc_b200_handle::kSlots && rc == KMC_B200_OK; ++s) {
+    if ((e = cudaStreamCreateWithFlags(&h->stream[s], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->done[s], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_in[s], bytes)) != cudaSuccess || (e = cudaMalloc(&h->d_out[s], bytes)) != cudaSuccess ||
+        (e = cudaMallocHost(&h->h_in[s], bytes)) != cudaSuccess || (e = cudaMallocHost(&h->h_out[s], bytes)) != cudaSuccess)
+      rc = FailCuda(e, "handle_create: allocating streams/buffers");
+  }
+  if (rc != KMC_B200_OK) {
+    std::string const keep = LastError();
+    FreeHandle(h);
+    LastError() = keep;
+    return rc;
+  }
+  *out = h;
+  return KMC_B200_OK;
+}
+
+int kmc_b200_handle_destroy(kmc_b200_handle* h) {
+  FreeHandle(h);
+  return KMC_B200_OK;
+}
+
+int kmc_b200_default_handle(int device, kmc_b200_handle** out) {
+  if (!out) return Fail(KMC_B200_ERR_NULL_POINTER, "default_handle: null output");
+  *out = nullptr;
+  if (device < 0 || device >= kMaxDevices) return Fail(KMC_B200_ERR_NO_DEVICE, "default_handle: device ordinal out of range");
+  static std::mutex mu;
+  static kmc_b200_handle* table[kMaxDevices] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (!table[device]) {
+    if (int rc = kmc_b200_handle_create(device, 250000, &table[device])) return rc;  // data_io.hpp:17 in the reference
+  }
+  *out = table[device];
+  return KMC_B200_OK;
+}
+
+int kmc_b200_handle_device(const kmc_b200_handle* h) { return h ? h->device : KMC_B200_ERR_NULL_POINTER; }
+int64_t kmc_b200_handle_capacity(const kmc_b200_handle* h) { return h ? h->capacity : KMC_B200_ERR_NULL_POINTER; }
+
+// ---- host entry points -------------------------------------------------------------------------------------------------
+int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, int64_t n, const kmc_b200_frame_params* params,
+                               int mode) {
+  TraceRange const trace("kmc_b200_deskew_frame_host");
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_host: null handle");
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_frame_host: negative n_points");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_frame_host: unknown time mode");
+  if (!params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_host: null params");
+  if (n == 0) return KMC_B200_OK;
+  if (!in || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_host: null point buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  kmc_b200_frame_params const P = *params;
+  return StreamThroughDevice(h, in, out, n, [&](int slot, int64_t, int64_t count) -> int {
+    auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(h->d_in[slot], h->d_out[slot], count, P, mode, cfg, h->sm_count, h->stream[slot]));
+    return KMC_B200_OK;
+  });
+}
+
+int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* in, float* out, const int64_t* offsets,
+                               const kmc_b200_frame_params* params, int32_t n_frames, int mode) {
+  TraceRange const trace("kmc_b200_deskew_batch_host");
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_host: null handle");
+  if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_host: negative n_frames");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_batch_host: unknown time mode");
+  if (n_frames == 0) return KMC_B200_OK;
+  if (!offsets || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_host: null table");
+  if (int rc = CheckOffsets(offsets, n_frames)) return rc;
+  int64_t const n_total = offsets[n_frames];
+  if (n_total == 0) return KMC_B200_OK;
+  if (!in || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_host: null point buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  if (int rc = EnsureTables(h, n_frames)) return rc;
+  // tables go up once, on slot 0's stream; the other slots wait for them through an event
+  KMC_CUDA_TRY(cudaMemcpyAsync(h->d_offsets, offsets, static_cast<size_t>(n_frames + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream[0]));
+  KMC_CUDA_TRY(cudaMemcpyAsync(h->d_params, params, static_cast<size_t>(n_frames) * sizeof(kmc_b200_frame_params), cudaMemcpyHostToDevice, h->stream[0]));
+  KMC_CUDA_TRY(cudaStreamSynchronize(h->stream[0]));
+  return StreamThroughDevice(h, in, out, n_total, [&](int slot, int64_t first, int64_t count) -> int {
+    auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[slot], h->d_out[slot], h->d_offsets, h->d_params, n_frames, count, first,
+                                                  n_total, mode, cfg, h->sm_count, h->stream[slot]));
+    return KMC_B200_OK;
+  });
+}
+
+int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_handles, const float* in, float* out,
+                                    const int64_t* offsets, const kmc_b200_frame_params* params, int32_t n_frames, int mode) {
+  TraceRange const trace("kmc_b200_deskew_batch_multi_gpu");
+  if (!handles || n_handles <= 0) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_multi_gpu: no handles");
+  if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_multi_gpu: negative n_frames");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_batch_multi_gpu: unknown time mode");
+  if (n_frames == 0) return KMC_B200_OK;
+  if (!offsets || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_multi_gpu: null table");
+  for (int32_t i = 0; i < n_handles; ++i) {
+    if (!handles[i]) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_multi_gpu: null handle");
+    for (int32_t j = 0; j < i; ++j)
+      if (handles[j]->device == handles[i]->device)
+        return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_multi_gpu: handles must live on distinct devices");
+  }
+  if (int rc = CheckOffsets(offsets, n_frames)) return rc;
+  std::vector<int> status(static_cast<size_t>(n_handles), KMC_B200_OK);
+  std::vector<std::string> message(static_cast<size_t>(n_handles));
+  std::vector<std::thread> workers;
+  for (int32_t i = 0; i < n_handles; ++i) {
+    workers.emplace_back([&, i] {
+      int64_t fb = 0, fe = 0;
+      kmc_b200_shard_range(n_frames, n_handles, i, &fb, &fe);
+      if (fe <= fb) return;
+      std::vector<int64_t> local(static_cast<size_t>(fe - fb + 1));
+      for (int64_t f = fb; f <= fe; ++f) local[static_cast<size_t>(f - fb)] = offsets[f] - offsets[fb];
+      status[i] = kmc_b200_deskew_batch_host(handles[i], in ? in + 4 * offsets[fb] : nullptr, out ? out + 4 * offsets[fb] : nullptr,
+                                             local.data(), params + fb, static_cast<int32_t>(fe - fb), mode);
+      if (status[i] != KMC_B200_OK) message[i] = LastError();
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (int32_t i = 0; i < n_handles; ++i)
+    if (status[i] != KMC_B200_OK) return Fail(status[i], "device " + std::to_string(handles[i]->device) + ": " + message[i]);
+  return KMC_B200_OK;
+}
+
+int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, const double* stamps, double* out, int64_t n, double t_start,
+                                   double t_end, double t_req, const kmc_b200_frame_params* params, int* flags_out) {
+  TraceRange const trace("kmc_b200_deskew_cloud_f64_host");
+  if (flags_out) *flags_out = 0;
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null handle");
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_cloud_f64_host: negative n_points");
+  if (!params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null params");
+  if (!(t_end > t_start)) return Fail(KMC_B200_ERR_EMPTY_INTERVAL, "deskew_cloud_f64_host: t_end <= t_start");
+  if (!(t_req >= t_start && t_req <= t_end)) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "deskew_cloud_f64_host: requested time outside [t_start, t_end]");
+  if (n == 0) return KMC_B200_OK;
+  if (!cloud || !stamps || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  size_t const col = static_cast<size_t>(n) * sizeof(double);
+  if (int rc = EnsureF64Scratch(h, 9 * col + 16)) return rc;
+  double* d = h->d_f64;  // cloud (4 columns) | stamps | result (4 columns) | flags
+  int* d_flags = reinterpret_cast<int*>(d + 9 * n);
+  cudaStream_t const st = h->stream[0];
+  int flags = 0;
+  cudaError_t e = cudaMemcpyAsync(d, cloud, 4 * col, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + 4 * n, stamps, col, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, sizeof(int), st);
+  if (e == cudaSuccess)
+    e = kmc_b200::dev::LaunchDeskewCloudF64(d, d + 4 * n, d + 5 * n, n, t_start, t_end, (t_req - t_start) / (t_end - t_start), *params, d_flags,
+                                            h->sm_count, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 5 * n, 4 * col, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaError_t const sync = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = sync;
+  if (e != cudaSuccess) return FailCuda(e, "deskew_cloud_f64_host");
+  if (flags_out) *flags_out = flags;
+  if (flags & 1) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "a point stamp lies outside [t_start, t_end] (reference asserts, trajectory_interpolation.cpp:32)");
+  if (flags & 2) return Fail(KMC_B200_ERR_BAD_SIZE, "the 4th cloud column must be the homogeneous 1 (data_types.hpp:13)");
+  return KMC_B200_OK;
+}
+
+int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n, double start, double end,
+                                        double* stamps) {
+  TraceRange const trace("kmc_b200_pseudo_time_stamps_xy_host");
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_xy_host: null handle");
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_xy_host: negative n_points");
+  if (n == 0) return KMC_B200_OK;
+  if (!x || !y || !stamps) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_xy_host: null argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  size_t const bytes = static_cast<size_t>(n) * sizeof(double);
+  if (int rc = EnsureF64Scratch(h, 3 * bytes)) return rc;
+  double* d = h->d_f64;  // x | y | stamps
+  cudaStream_t const st = h->stream[0];
+  cudaError_t e = cudaMemcpyAsync(d, x, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, y, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = kmc_b200::dev::LaunchPseudoTimeStampsXy(d, d + n, d + 2 * n, n, start, end, h->sm_count, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(stamps, d + 2 * n, bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return FailCuda(e, "pseudo_time_stamps_xy_host");
+  return KMC_B200_OK;
+}
+
+int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* in, float* uvzc_out, int64_t n, const kmc_b200_camera_params* camera) {
+  TraceRange const trace("kmc_b200_project_frame_host");
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "project_frame_host: null handle");
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "project_frame_host: negative n_points");
+  if (!camera) return Fail(KMC_B200_ERR_NULL_POINTER, "project_frame_host: null camera params");
+  if (n == 0) return KMC_B200_OK;
+  if (!in || !uvzc_out) return Fail(KMC_B200_ERR_NULL_POINTER, "project_frame_host: null point buffer");
+  if (in == uvzc_out) return Fail(KMC_B200_ERR_BAD_SIZE, "project_frame_host: the pixel buffer must not alias the cloud");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  kmc_b200_camera_params const K = *camera;
+  return StreamThroughDevice(h, in, uvzc_out, n, [&](int slot, int64_t, int64_t count) -> int {
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchProject(h->d_in[slot], nullptr, h->d_out[slot], count, nullptr, K, KMC_B200_TIME_FROM_AZIMUTH, true,
+                                              h->sm_count, h->stream[slot]));
+    return KMC_B200_OK;
+  });
+}
+
+int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out, const kmc_b200_frame_params* params,
+                             int64_t* n_points_out) {
+  TraceRange const trace("kmc_b200_deskew_bin_file");
+  if (!h || !path_in || !path_out || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_file: null argument");
+  FILE* f = std::fopen(path_in, "rb");
+  if (!f) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path_in);
+  std::fseek(f, 0, SEEK_END);
+  long const size = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  if (size < 0 || size % 16 != 0) {
+    std::fclose(f);
+    return Fail(KMC_B200_ERR_IO, std::string("KITTI pointcloud binary file is not a whole number of xyzi points: ") + path_in);
+  }
+  int64_t const n = size / 16;
+  std::vector<float> buf(static_cast<size_t>(4 * n)), res(static_cast<size_t>(4 * n));
+  size_t const got = n ? std::fread(buf.data(), 16, static_cast<size_t>(n), f) : 0;
+  std::fclose(f);
+  if (static_cast<int64_t>(got) != n) return Fail(KMC_B200_ERR_IO, std::string("short read: ") + path_in);
+  if (int rc = kmc_b200_deskew_frame_host(h, buf.data(), res.data(), n, params, KMC_B200_TIME_FROM_AZIMUTH)) return rc;
+  FILE* g = std::fopen(path_out, "wb");
+  if (!g) return Fail(KMC_B200_ERR_IO, std::string("unable to create output file: ") + path_out);
+  size_t const put = n ? std::fwrite(res.data(), 16, static_cast<size_t>(n), g) : 0;
+  bool const closed = (std::fclose(g) == 0);
+  if (static_cast<int64_t>(put) != n || !closed) return Fail(KMC_B200_ERR_IO, std::string("short write: ") + path_out);
+  if (n_points_out) *n_points_out = n;
+  return KMC_B200_OK;
+}
+
+
+// ---- many KITTI .bin files through one overlapped pipeline ------------------------------------------------------------------
+namespace {
+
+// Runs fn(0..n_items-1) on up to n_threads short-lived host threads; returns the first non-zero status.
+int ParallelFor(int64_t n_items, int n_threads, const std::function<int(int64_t)>& fn) {
+  if (n_items <= 0) return KMC_B200_OK;
+  n_threads = static_cast<int>(std::min<int64_t>(std::max(n_threads, 1), n_items));
+  std::atomic<int64_t> next{0};
+  std::atomic<int> status{KMC_B200_OK};
+  std::string message;
+  std::mutex message_mu;
+  auto body = [&] {
+    for (;;) {
+      int64_t const i = next.fetch_add(1);
+      if (i >= n_items || status.load() != KMC_B200_OK) return;
+      int const rc = fn(i);
+      if (rc != KMC_B200_OK) {
+        std::lock_guard<std::mutex> lock(message_mu);
+        if (status.load() == KMC_B200_OK) {
+          message = LastError();  // Fail() wrote it on this worker thread
+          status.store(rc);
+        }
+      }
+    }
+  };
+  if (n_threads == 1) {
+    body();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(body);
+    for (auto& th : pool) th.join();
+  }
+  if (status.load() != KMC_B200_OK) LastError() = message;
+  return status.load();
+}
+
+int ReadWholeFile(const char* path, void* dst, size_t bytes) {
+  int const fd = ::open(path, O_RDONLY | O_CLOEXEC);
+  if (fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path);
+  size_t done = 0;
+  while (done < bytes) {
+    ssize_t const got = ::pread(fd, static_cast<char*>(dst) + done, bytes - done, static_cast<off_t>(done));
+    if (got < 0 && errno == EINTR) continue;
+    if (got <= 0) break;
+    done += static_cast<size_t>(got);
+  }
+  ::close(fd);
+  if (done != bytes) return Fail(KMC_B200_ERR_IO, std::string("short read: ") + path);
+  return KMC_B200_OK;
+}
+
+int WriteWholeFile(const char* path, const void* src, size_t bytes) {
+  int const fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+  if (fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to create output file: ") + path);
+  size_t done = 0;
+  while (done < bytes) {
+    ssize_t const put = ::pwrite(fd, static_cast<const char*>(src) + done, bytes - done, static_cast<off_t>(done));
+    if (put < 0 && errno == EINTR) continue;
+    if (put <= 0) break;
+    done += static_cast<size_t>(put);
+  }
+  bool const closed = (::close(fd) == 0);
+  if (done != bytes || !closed) return Fail(KMC_B200_ERR_IO, std::string("short write: ") + path);
+  return KMC_B200_OK;
+}
+
+}  // namespace
+
+// Files are packed, in order, into groups that fit one staging slot of the handle.  Three slots rotate through
+//   read (io_threads x pread straight into the slot's pinned input buffer)  ->  H2D  ->  batched deskew kernel  ->  D2H
+//   ->  write (io_threads x pwrite straight from the slot's pinned output buffer),
+// the calling thread doing the reads and the launches, one helper thread retiring slots (event wait + writes), so the
+// disk / page cache, both PCIe directions and the SMs are busy at the same time.  No intermediate host copies: the .bin
+// format is the kernel's input layout.
+int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* const* paths_in, const char* const* paths_out,
+                              const kmc_b200_frame_params* params, int mode, int32_t io_threads, int64_t* points_out) {
+  TraceRange const trace("kmc_b200_deskew_bin_files");
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_files: null handle");
+  if (n_files < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_bin_files: negative n_files");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_bin_files: unknown time mode");
+  if (n_files == 0) return KMC_B200_OK;
+  if (!paths_in || !paths_out || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_files: null argument");
+  if (io_threads <= 0) io_threads = static_cast<int32_t>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+  constexpr int kSlots = kmc_b200_handle::kSlots;
+
+  // sizes, global offsets, groups
+  std::vector<int64_t> offsets(static_cast<size_t>(n_files) + 1, 0);
+  for (int32_t f = 0; f < n_files; ++f) {
+    if (!paths_in[f] || !paths_out[f]) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_files: null path");
+    struct stat st;
+    if (::stat(paths_in[f], &st) != 0) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + paths_in[f]);
+    if (st.st_size % 16 != 0)
+      return Fail(KMC_B200_ERR_IO, std::string("KITTI pointcloud binary file is not a whole number of xyzi points: ") + paths_in[f]);
+    int64_t const n = static_cast<int64_t>(st.st_size / 16);
+    offsets[static_cast<size_t>(f) + 1] = offsets[static_cast<size_t>(f)] + n;
+    if (points_out) points_out[f] = n;
+  }
+  struct Group {
+    int32_t first_file, end_file;
+  };
+  std::vector<Group> groups;
+  for (int32_t f = 0; f < n_files;) {
+    int32_t e = f + 1;
+    while (e < n_files && offsets[static_cast<size_t>(e) + 1] - offsets[static_cast<size_t>(f)] <= h->capacity) ++e;
+    groups.push_back({f, e});
+    f = e;
+  }
+  int64_t const n_total = offsets[static_cast<size_t>(n_files)];
+
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  if (int rc = EnsureTables(h, n_files)) return rc;
+  KMC_CUDA_TRY(cudaMemcpyAsync(h->d_offsets, offsets.data(), offsets.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream[0]));
+  KMC_CUDA_TRY(cudaMemcpyAsync(h->d_params, params, static_cast<size_t>(n_files) * sizeof(kmc_b200_frame_params), cudaMemcpyHostToDevice, h->stream[0]));
+  KMC_CUDA_TRY(cudaStreamSynchronize(h->stream[0]));
+
+  // slot hand-over between the submitting (this) thread and the retiring thread
+  std::mutex mu;
+  std::condition_variable cv;
+  bool slot_free[kSlots];
+  for (bool& b : slot_free) b = true;
+  std::deque<size_t> submitted;  // group indices in submission order
+  bool no_more = false;
+  int retire_status = KMC_B200_OK;
+  std::string retire_message;
+
+  std::thread retirer([&] {
+    cudaSetDevice(h->device);
+    for (;;) {
+      size_t g;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !submitted.empty() || no_more; });
+        if (submitted.empty()) return;
+        g = submitted.front();
+        submitted.pop_front();
+      }
+      int const slot = static_cast<int>(g % kSlots);
+      int rc = KMC_B200_OK;
+      cudaError_t const e = cudaEventSynchronize(h->done[slot]);
+      if (e != cudaSuccess) rc = FailCuda(e, "cudaEventSynchronize(done)");
+      if (rc == KMC_B200_OK) {
+        Group const grp = groups[g];
+        int64_t const base = offsets[static_cast<size_t>(grp.first_file)];
+        rc = ParallelFor(grp.end_file - grp.first_file, io_threads, [&](int64_t k) -> int {
+          size_t const f = static_cast<size_t>(grp.first_file + k);
+          return WriteWholeFile(paths_out[f], h->h_out[slot] + 4 * (offsets[f] - base), static_cast<size_t>(offsets[f + 1] - offsets[f]) * 16);
+        });
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (rc != KMC_B200_OK && retire_status == KMC_B200_OK) {
+          retire_status = rc;
+          retire_message = LastError();
+        }
+        slot_free[slot] = true;
+      }
+      cv.notify_all();
+    }
+  });
+
+  int status = KMC_B200_OK;
+  for (size_t g = 0; g < groups.size() && status == KMC_B200_OK; ++g) {
+    int const slot = static_cast<int>(g % kSlots);
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return slot_free[slot]; });
+      if (retire_status != KMC_B200_OK) break;
+      slot_free[slot] = false;
+    }
+    Group const grp = groups[g];
+    int64_t const base = offsets[static_cast<size_t>(grp.first_file)];
+    int64_t const count = offsets[static_cast<size_t>(grp.end_file)] - base;
+    if (count > h->capacity) {
+      // One file larger than a staging slot (a group of its own): let the pipeline drain, then stream the file through all
+      // three slots in capacity-sized chunks, as kmc_b200_deskew_batch_host does for an array.
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        slot_free[slot] = true;
+        cv.wait(lk, [&] { return submitted.empty() && std::all_of(slot_free, slot_free + kSlots, [](bool b) { return b; }); });
+        if (retire_status != KMC_B200_OK) break;
+      }
+      size_t const f = static_cast<size_t>(grp.first_file);
+      std::vector<float> big_in(static_cast<size_t>(count) * 4), big_out(static_cast<size_t>(count) * 4);
+      status = ReadWholeFile(paths_in[f], big_in.data(), static_cast<size_t>(count) * 16);
+      if (status == KMC_B200_OK)
+        status = StreamThroughDevice(h, big_in.data(), big_out.data(), count, [&](int s, int64_t first, int64_t chunk) -> int {
+          auto const cfg = kmc_b200::dev::PickConfig(chunk, true, false, h->sm_count);
+          KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[s], h->d_out[s], h->d_offsets, h->d_params, n_files, chunk, base + first,
+                                                        n_total, mode, cfg, h->sm_count, h->stream[s]));
+          return KMC_B200_OK;
+        });
+      if (status == KMC_B200_OK) status = WriteWholeFile(paths_out[f], big_out.data(), static_cast<size_t>(count) * 16);
+      continue;
+    }
+    status = ParallelFor(grp.end_file - grp.first_file, io_threads, [&](int64_t k) -> int {
+      size_t const f = static_cast<size_t>(grp.first_file + k);
+      return ReadWholeFile(paths_in[f], h->h_in[slot] + 4 * (offsets[f] - base), static_cast<size_t>(offsets[f + 1] - offsets[f]) * 16);
+    });
+    auto submit = [&]() -> int {
+      if (count > 0) {
+        size_t const bytes = static_cast<size_t>(count) * 16;
+        KMC_CUDA_TRY(cudaMemcpyAsync(h->d_in[slot], h->h_in[slot], bytes, cudaMemcpyHostToDevice, h->stream[slot]));
+        auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
+        KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[slot], h->d_out[slot], h->d_offsets, h->d_params, n_files, count, base,
+                                                      n_total, mode, cfg, h->sm_count, h->stream[slot]));
+        KMC_CUDA_TRY(cudaMemcpyAsync(h->h_out[slot], h->d_out[slot], bytes, cudaMemcpyDeviceToHost, h->stream[slot]));
+      }
+      KMC_CUDA_TRY(cudaEventRecord(h->done[slot], h->stream[slot]));
+      return KMC_B200_OK;
+    };
+    if (status == KMC_B200_OK) status = submit();
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (status == KMC_B200_OK) submitted.push_back(g);
+      else slot_free[slot] = true;
+    }
+    cv.notify_all();
+  }
+  std::string const keep = LastError();
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    no_more = true;
+  }
+  cv.notify_all();
+  retirer.join();
+  if (status != KMC_B200_OK) {
+    for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
+    cudaGetLastError();
+    LastError() = keep;
+    return status;
+  }
+  if (retire_status != KMC_B200_OK) {
+    LastError() = retire_message;
+    return retire_status;
+  }
+  return KMC_B200_OK;
+}
+
+}  // extern "C"

@@ -80,6 +80,10 @@ __device__ __forceinline__ Point2 LoadPoint2(const float4* p) {
     asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
                  : "l"(p));
+  } else if constexpr (HINT == 3 || HINT == 5 || HINT == 6) {  // experiment: L2 eviction priority (SASS LDG.E.EFL2.256)
+    asm volatile("ld.global.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+                 : "l"(p));
   } else {
     asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
@@ -96,6 +100,14 @@ __device__ __forceinline__ void StorePoint2(float4* p, const Point2& v) {
                  : "memory");
   } else if constexpr (HINT == 2) {
     asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.a.x), "f"(v.a.y), "f"(v.a.z),
+                 "f"(v.a.w), "f"(v.b.x), "f"(v.b.y), "f"(v.b.z), "f"(v.b.w)
+                 : "memory");
+  } else if constexpr (HINT == 4 || HINT == 6) {  // STG.E.EFL2.256
+    asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.a.x), "f"(v.a.y), "f"(v.a.z),
+                 "f"(v.a.w), "f"(v.b.x), "f"(v.b.y), "f"(v.b.z), "f"(v.b.w)
+                 : "memory");
+  } else if constexpr (HINT == 5) {  // STG.E.ELL2.256
+    asm volatile("st.global.L2::evict_last.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.a.x), "f"(v.a.y), "f"(v.a.z),
                  "f"(v.a.w), "f"(v.b.x), "f"(v.b.y), "f"(v.b.z), "f"(v.b.w)
                  : "memory");
   } else {
@@ -470,7 +482,7 @@ template <int MODE>
 cudaError_t DispatchFrame(const float* in, float* out, int64_t n, const kmc_b200_frame_params& P, const LaunchConfig& cfg,
                           int sm, cudaStream_t st) {
 #define KMC_FRAME_CALL(V, U)                                                                          \
-  return cfg.hint ? DispatchFrameBlock<MODE, V, U, 1>(in, out, n, P, cfg, sm, st)                     \
+  return cfg.hint == 1 ? DispatchFrameBlock<MODE, V, U, 1>(in, out, n, P, cfg, sm, st)                \
                   : DispatchFrameBlock<MODE, V, U, 0>(in, out, n, P, cfg, sm, st);
   if (cfg.vec == 2) {
     if (cfg.unroll >= 2) { KMC_FRAME_CALL(2, 2) }
@@ -495,8 +507,16 @@ cudaError_t DispatchBatch(const float* in, float* out, const int64_t* offsets, c
                           int32_t n_frames, int64_t n, int64_t base, int64_t nb, const LaunchConfig& cfg, int sm,
                           cudaStream_t st) {
 #define KMC_BATCH_CALL(V, U)                                                                                              \
-  return cfg.hint ? DispatchBatchBlock<MODE, V, U, 1>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st)         \
+  return cfg.hint == 1 ? DispatchBatchBlock<MODE, V, U, 1>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st)    \
                   : DispatchBatchBlock<MODE, V, U, 0>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);
+  if (cfg.vec == 2 && cfg.hint >= 3) {  // L2 eviction-priority experiments (256-bit accesses only)
+    switch (cfg.hint) {
+      case 3: return DispatchBatchBlock<MODE, 2, 1, 3>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);
+      case 4: return DispatchBatchBlock<MODE, 2, 1, 4>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);
+      case 5: return DispatchBatchBlock<MODE, 2, 1, 5>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);
+      default: return DispatchBatchBlock<MODE, 2, 1, 6>(in, out, offsets, table, n_frames, n, base, nb, cfg, sm, st);
+    }
+  }
   if (cfg.vec == 2) {
     if (cfg.unroll >= 2) { KMC_BATCH_CALL(2, 2) }
     KMC_BATCH_CALL(2, 1)
@@ -573,7 +593,7 @@ LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_
   if (in_place && cfg.hint == 1) cfg.hint = 0;  // the .nc path assumes the input is read-only for the whole kernel
   if (cfg.vec != 2) cfg.vec = 1;
   if (cfg.unroll < 1) cfg.unroll = 1;
-  if (cfg.hint < 0 || cfg.hint > 1) cfg.hint = 0;
+  if (cfg.hint < 0 || cfg.hint > 6 || cfg.hint == 2) cfg.hint = 0;  // 3-6: L2 eviction-priority experiments (batch kernel)
   if (cfg.block != 128 && cfg.block != 512) cfg.block = 256;
   if (cfg.ctas_per_sm < 1) cfg.ctas_per_sm = 1;
   if (cfg.ctas_per_sm > 16) cfg.ctas_per_sm = 16;

@@ -6,6 +6,9 @@
  *   TrajectoryInterpolator            include/kitti_motion_compensation/trajectory_interpolation.hpp:11-31
  *   kmc::lie::{Exp,Log,...}           include/kitti_motion_compensation/lie_algebra.hpp:12-26
  *   kmc::GetPseudoTimeStamps          include/kitti_motion_compensation/timestamp_mocking.hpp:7-11
+ * and the rows either side of it: KITTI .bin files as the kernel's I/O (data_io.hpp:19-83, data_io.cpp:287-313),
+ * OxtsToPose / MakeFrame (data_io.hpp:13, 89-90), the whole-run handler (handlers.hpp:11) and the projection onto the
+ * cameras (camera_model.hpp:7-11).
  * (citations are relative to the reference repository root).  The reference has no FFI of its own — its boundary is
  * a C++ shared library with Eigen types in the signatures — so this header is what a binding of that path would
  * bind: plain pointers, sizes and doubles, no C++/Eigen/torch types.  The headers under include/kitti_motion_compensation/ hold

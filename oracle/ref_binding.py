@@ -60,6 +60,7 @@ def lib() -> C.CDLL:
         _lib.kmc_ref_write_pointcloud.argtypes = [C.c_char_p, C.c_int64, _dp, _dp, C.c_int64]
         _lib.kmc_ref_motion_compensate_run.restype = C.c_double
         _lib.kmc_ref_motion_compensate_run.argtypes = [C.c_char_p]
+        _lib.kmc_ref_load_calibration.argtypes = [C.c_char_p, _dp, _dp, _dp, _dp]
         _lib.kmc_ref_project_pointcloud_on_frame.argtypes = [_dp, C.c_int64, _dp, _dp, _dp, C.POINTER(C.POINTER(C.c_int32)),
                                                              C.POINTER(_dp), C.POINTER(C.c_int64)]
     return _lib
@@ -273,3 +274,14 @@ def project_pointcloud_on_frame(cloud_n4, tf_c00_lo, R_rect_00, P_rects):
     lib().kmc_ref_project_pointcloud_on_frame(_ptr(_colmajor(cloud)), n, _ptr(_colmajor(tf_c00_lo)), _ptr(_colmajor(R_rect_00)), _ptr(P),
                                               uv_ptrs, col_ptrs, counts)
     return [(uv[k][:counts[k]].copy(), col[k][:counts[k]].copy()) for k in range(4)]
+
+
+def load_calibration(folder):
+    """LoadLidarExtrinsics(folder, to_cam=True) + LoadCameraCalibrations(folder) (data_io.cpp:168-210, 321-406).
+    Returns (T_velo_to_cam 4x4, R_rect_00 3x3, [P_rect_00..03] 3x4, S_rect_00 (2,))."""
+    for name in ("calib_velo_to_cam.txt", "calib_cam_to_cam.txt"):
+        if not os.path.exists(os.path.join(folder, name)):
+            raise FileNotFoundError(os.path.join(folder, name))  # the reference prints and exit(0)s
+    T, R, P, S = np.empty(16), np.empty(9), np.empty(48), np.empty(2)
+    lib().kmc_ref_load_calibration(os.fsencode(folder), _ptr(T), _ptr(R), _ptr(P), _ptr(S))
+    return _from_colmajor(T, 4), _from_colmajor(R, 3), [P[12 * k:12 * k + 12].reshape(4, 3).T.copy() for k in range(4)], S

@@ -277,4 +277,19 @@ void kmc_ref_project_pointcloud_on_frame(const double* cloud_colmajor, int64_t n
   }
 }
 
+
+// LoadLidarExtrinsics + LoadCameraCalibrations (data_io.cpp:168-210, 321-406) on a KITTI calibration folder: the
+// velodyne -> camera_00 transform, R_rect_00, the four P_rect (3x4, column-major each) and S_rect_00.
+void kmc_ref_load_calibration(const char* folder, double T_velo_to_cam[16], double R_rect_00[9], double P_rect[4][12], double S_rect_00[2]) {
+  AffineOut(kmc::LoadLidarExtrinsics(kmc::Path(folder), true), T_velo_to_cam);
+  kmc::viz::CameraCalibrations const c{kmc::viz::LoadCameraCalibrations(kmc::Path(folder))};
+  kmc::viz::CameraCalibration const* cams[4] = {&c.camera_00, &c.camera_01, &c.camera_02, &c.camera_03};
+  Mat3Out(c.camera_00.R_rect, R_rect_00);
+  for (int k = 0; k < 4; ++k)
+    for (int col = 0; col < 4; ++col)
+      for (int r = 0; r < 3; ++r) P_rect[k][col * 3 + r] = cams[k]->P_rect(r, col);
+  S_rect_00[0] = c.camera_00.S_rect(0);
+  S_rect_00[1] = c.camera_00.S_rect(1);
+}
+
 }  // extern "C"

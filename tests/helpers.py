@@ -163,3 +163,22 @@ def make_run_folder(root: str, n_frames: int = 6, points: int = 20_000, seed: in
 
 def read_bin(path: str) -> np.ndarray:
     return np.fromfile(path, dtype=np.float32).reshape(-1, 4)
+
+
+def write_calibration_folder(root: str, calib: dict) -> None:
+    """calib_velo_to_cam.txt + calib_cam_to_cam.txt in the KITTI raw format (data_io.cpp:168-210, 321-406 read them):
+    a header line (two for cam_to_cam), then `label: numbers` lines; each camera block is S K D R T S_rect R_rect P_rect."""
+    def line(label, values):
+        return f"{label}: " + " ".join(f"{v:.6e}" for v in values)
+    os.makedirs(root, exist_ok=True)
+    with open(os.path.join(root, "calib_velo_to_cam.txt"), "w") as f:
+        f.write("calib_time: 15-Mar-2012 11:37:16\n" + line("R", calib["velo_to_cam"]["R"]) + "\n" + line("T", calib["velo_to_cam"]["T"])
+                + "\ndelta_f: 0.000000e+00 0.000000e+00\ndelta_c: 0.000000e+00 0.000000e+00\n")
+    with open(os.path.join(root, "calib_cam_to_cam.txt"), "w") as f:
+        f.write("calib_time: 09-Jan-2012 13:57:47\ncorner_dist: 9.950000e-02\n")
+        for k in ("00", "01", "02", "03"):
+            f.write(line(f"S_{k}", [1392.0, 512.0]) + "\n" + line(f"K_{k}", [984.2439, 0, 690.0, 0, 980.8141, 233.1966, 0, 0, 1]) + "\n"
+                    + line(f"D_{k}", [-0.3728755, 0.2037299, 0.002219027, 0.001383707, -0.07233722]) + "\n"
+                    + line(f"R_{k}", [1, 0, 0, 0, 1, 0, 0, 0, 1]) + "\n" + line(f"T_{k}", [-0.5 * int(k), 0, 0]) + "\n"
+                    + line(f"S_rect_{k}", calib["S_rect_00"]) + "\n" + line(f"R_rect_{k}", calib["R_rect_00"]) + "\n"
+                    + line(f"P_rect_{k}", calib["P_rect"][k]) + "\n")

@@ -219,3 +219,20 @@ def test_projection_draw_list_against_the_oracle():
         assert np.array_equal(uv[valid].astype(np.int32), ref_uv)                 # cv::Point truncation
         assert np.abs(ref_col[:, 1] - color[valid]).max() < 1e-9
         assert np.abs(ref_col[:, 0] - (255.0 - color[valid])).max() < 1e-9 and np.array_equal(ref_col[:, 0], ref_col[:, 2])
+
+
+def test_calibration_parsers(tmp_path):
+    """LoadLidarExtrinsics / LoadCameraCalibrations (data_io.cpp:168-210, 321-406) compiled from the reference read back the
+    calibration the projection tests use (tests/golden/kitti_calibration_2011_09_26.json, written out in KITTI's text format)."""
+    import json
+    import os
+    with open(os.path.join(h.GOLDEN, "kitti_calibration_2011_09_26.json")) as f:
+        c = json.load(f)
+    h.write_calibration_folder(str(tmp_path), c)
+    T, R_rect, P, S = rb.load_calibration(str(tmp_path))
+    assert np.allclose(T[:3, :3], np.array(c["velo_to_cam"]["R"]).reshape(3, 3), rtol=1e-7, atol=0)
+    assert np.allclose(T[:3, 3], c["velo_to_cam"]["T"], rtol=1e-7, atol=0) and np.array_equal(T[3], [0, 0, 0, 1])
+    assert np.allclose(R_rect, np.array(c["R_rect_00"]).reshape(3, 3), rtol=1e-7, atol=0)
+    for k, name in enumerate(("00", "01", "02", "03")):
+        assert np.allclose(P[k], np.array(c["P_rect"][name]).reshape(3, 4), rtol=1e-7, atol=0)
+    assert np.allclose(S, c["S_rect_00"])

@@ -1,7 +1,8 @@
 # Build without Python (the same commands kitti_motion_compensation_b200/build.py runs).
 #   make            libkmc_b200.so (CUDA kernels + C ABI, sm_100a) and libkitti_motion_compensation_lib.so (C++ mirror)
 #   make example    lib/motion_compensate_runs (the reference's CLI on top of the mirror)
-#   make oracle     oracle/libkmc_oracle.so (CPU restatement — test infrastructure only)
+#   make oracle     oracle/libkmc_oracle.so (CPU restatement) and, where /root/reference exists, oracle/_ref/libkmc_ref.so (the
+#                   reference's own sources compiled unmodified) — test infrastructure only
 #   make cpp-tests  tests/cpp/_build/test_{dropin_host,dropin_gpu,eigen_shim}
 NVCC      ?= nvcc
 CXX       ?= g++
@@ -31,6 +32,7 @@ $(LIB)/motion_compensate_runs: examples/motion_compensate_runs.cpp $(LIB)/libkit
 
 oracle:
 	$(MAKE) -C oracle
+	$(MAKE) -C oracle ref
 
 cpp-tests: all
 	@mkdir -p tests/cpp/_build

@@ -273,6 +273,15 @@ typedef struct kmc_b200_run_stats {
   double seconds_total;
 } kmc_b200_run_stats;
 
+/* The host half of MotionCompensateRun, no GPU involved: counts the frames of a KITTI raw run folder (every entry of
+ * velodyne_points/data, handlers.cpp:15-17) and builds the per-frame kernel records of frames 1 .. n-2 — LoadTimeStamp /
+ * LoadOxts / OxtsToPose / MakeFrame (data_io.cpp:18-88, 253-269) with every text file read once, then
+ * kmc_b200_frame_params_from_poses with the camera-trigger time as the requested time (handlers.cpp:59).
+ * params_out (capacity_frames records, may be NULL to only count) receives n_frames - 2 records; record k belongs to frame k + 1.
+ * Statuses as kmc_b200_motion_compensate_run. */
+KMC_B200_API int kmc_b200_run_prepare(const char* run_folder, int64_t capacity_frames, kmc_b200_frame_params* params_out,
+                                      int64_t* n_frames_out);
+
 /* MotionCompensateRun (handlers.cpp:41-65) on a KITTI raw run folder: reads oxts/timestamps.txt, every oxts/data packet and
  * velodyne_points/{timestamps_start,timestamps,timestamps_end}.txt once, builds every frame's start/end pose as MakeFrame
  * does (data_io.cpp:253-269), deskews frames 1 .. n-2 to their camera-trigger time through kmc_b200_deskew_bin_files into

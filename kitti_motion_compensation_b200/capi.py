@@ -120,6 +120,7 @@ SIGNATURES = {
     "kmc_b200_deskew_bin_files": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _vp, C.c_int, C.c_int32,
                                             C.POINTER(C.c_int64)]),
     "kmc_b200_motion_compensate_run": (C.c_int, [_vp, C.c_char_p, C.c_int32, _vp]),
+    "kmc_b200_run_prepare": (C.c_int, [C.c_char_p, C.c_int64, _vp, C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -410,6 +411,16 @@ class Handle:
         stats = RunStats()
         check(lib().kmc_b200_motion_compensate_run(self._h, os.fsencode(run_folder), io_threads, C.byref(stats)))
         return {name: getattr(stats, name) for name, _ in RunStats._fields_}
+
+
+def run_prepare(run_folder: str):
+    """Host half of MotionCompensateRun (no GPU): (n_frames, per-frame records of frames 1 .. n-2)."""
+    n = C.c_int64(0)
+    check(lib().kmc_b200_run_prepare(os.fsencode(run_folder), 0, None, C.byref(n)))
+    params = np.zeros(max(n.value - 2, 0), dtype=FRAME_PARAMS_DTYPE)
+    if params.size:
+        check(lib().kmc_b200_run_prepare(os.fsencode(run_folder), params.size, params.ctypes.data, C.byref(n)))
+    return n.value, params
 
 
 def deskew_batch_multi_gpu(handles: list[Handle], xyzi: np.ndarray, offsets: np.ndarray, params: np.ndarray,

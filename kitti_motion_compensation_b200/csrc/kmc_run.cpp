@@ -1,4 +1,5 @@
-// kmc_run.cpp — kmc_b200_motion_compensate_run: a whole KITTI raw run folder through the deskew pipeline.
+// kmc_run.cpp — kmc_b200_run_prepare / kmc_b200_motion_compensate_run: a whole KITTI raw run folder through the deskew
+// pipeline, split into its host half (text files -> per-frame records, no GPU) and the file pipeline.
 //
 // Reference: handlers.cpp:41-65 (MotionCompensateRun), :19-39 (first / last frame copy), data_io.cpp:18-66 (LoadTimeStamp,
 // LoadOxts), :140-166 (LoadLidarScan), :253-285 (MakeFrame, LoadSingleFrame), utils.cpp:9-41 (id padding, tokenizer, clock
@@ -84,21 +85,67 @@ double Seconds(std::chrono::steady_clock::time_point a) {
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
 }
 
+// Everything MotionCompensateRun needs before the first scan is touched: the number of frames and, for the frames
+// 1 .. n-2 that have an OxTS packet on both sides, the per-frame kernel record.
+int PrepareRun(fs::path const& run, size_t* n_out, std::vector<kmc_b200_frame_params>* params) {
+  fs::path const velodyne{run / "velodyne_points"};
+  fs::path const data{velodyne / "data"};
+  std::error_code ec;
+  if (!fs::is_directory(data, ec)) return SetError(KMC_B200_ERR_IO, "not a KITTI run folder (no velodyne_points/data): " + run.string());
+  size_t n = 0;  // handlers.cpp:15-17: every directory entry counts as a frame
+  for (auto it = fs::directory_iterator(data, ec); !ec && it != fs::directory_iterator(); it.increment(ec)) ++n;
+  if (ec) return SetError(KMC_B200_ERR_IO, "unable to list " + data.string() + ": " + ec.message());
+  *n_out = n;
+  params->clear();
+  if (n < 3) return KMC_B200_OK;
+  std::vector<double> start, middle, end, oxts_time;
+  if (int rc = LoadTimeStamps(velodyne / "timestamps_start.txt", n, &start)) return rc;
+  if (int rc = LoadTimeStamps(velodyne / "timestamps.txt", n, &middle)) return rc;
+  if (int rc = LoadTimeStamps(velodyne / "timestamps_end.txt", n, &end)) return rc;
+  if (int rc = LoadTimeStamps(run / "oxts" / "timestamps.txt", n, &oxts_time)) return rc;
+  std::vector<double> pose(16 * n);
+  for (size_t i = 0; i < n; ++i)
+    if (int rc = LoadOxtsPose(run / "oxts" / "data" / (PaddedId(i) + ".txt"), &pose[16 * i])) return rc;
+  params->resize(n - 2);
+  for (size_t i = 1; i + 1 < n; ++i) {
+    double T_start[16], T_end[16];
+    // MakeFrame: the scan's start lies between packets i-1 and i, its end between packets i and i+1
+    int rc = kmc_b200_pose_at_time(oxts_time[i - 1], &pose[16 * (i - 1)], oxts_time[i], &pose[16 * i], start[i], T_start);
+    if (rc == KMC_B200_OK) rc = kmc_b200_pose_at_time(oxts_time[i], &pose[16 * i], oxts_time[i + 1], &pose[16 * (i + 1)], end[i], T_end);
+    if (rc == KMC_B200_OK) rc = kmc_b200_frame_params_from_poses(T_start, T_end, start[i], end[i], middle[i], &(*params)[i - 1]);
+    if (rc != KMC_B200_OK) return SetError(rc, "frame " + std::to_string(i) + ": " + kmc_b200_last_error());
+  }
+  return KMC_B200_OK;
+}
+
 }  // namespace
+
+extern "C" int kmc_b200_run_prepare(const char* run_folder, int64_t capacity_frames, kmc_b200_frame_params* params_out,
+                                    int64_t* n_frames_out) {
+  if (!run_folder || !n_frames_out) return SetError(KMC_B200_ERR_NULL_POINTER, "run_prepare: null argument");
+  size_t n = 0;
+  std::vector<kmc_b200_frame_params> params;
+  if (int rc = PrepareRun(fs::path{run_folder}, &n, &params)) return rc;
+  *n_frames_out = static_cast<int64_t>(n);
+  if (params_out) {
+    if (capacity_frames < static_cast<int64_t>(params.size()))
+      return SetError(KMC_B200_ERR_CAPACITY, "run_prepare: params_out holds fewer than n_frames - 2 records");
+    for (size_t k = 0; k < params.size(); ++k) params_out[k] = params[k];
+  }
+  return KMC_B200_OK;
+}
 
 extern "C" int kmc_b200_motion_compensate_run(kmc_b200_handle* h, const char* run_folder, int32_t io_threads,
                                               kmc_b200_run_stats* stats) {
   if (!h || !run_folder) return SetError(KMC_B200_ERR_NULL_POINTER, "motion_compensate_run: null argument");
   auto const t_begin = std::chrono::steady_clock::now();
   fs::path const run{run_folder};
-  fs::path const velodyne{run / "velodyne_points"};
-  fs::path const data{velodyne / "data"};
-  fs::path const out_dir{velodyne / "data_motion_compensated"};
+  fs::path const data{run / "velodyne_points" / "data"};
+  fs::path const out_dir{run / "velodyne_points" / "data_motion_compensated"};
+  size_t n = 0;
+  std::vector<kmc_b200_frame_params> params;
+  if (int rc = PrepareRun(run, &n, &params)) return rc;
   std::error_code ec;
-  if (!fs::is_directory(data, ec)) return SetError(KMC_B200_ERR_IO, "not a KITTI run folder (no velodyne_points/data): " + run.string());
-  size_t n = 0;  // handlers.cpp:15-17: every directory entry counts as a frame
-  for (auto it = fs::directory_iterator(data, ec); !ec && it != fs::directory_iterator(); it.increment(ec)) ++n;
-  if (ec) return SetError(KMC_B200_ERR_IO, "unable to list " + data.string() + ": " + ec.message());
   fs::create_directories(out_dir, ec);
   if (ec) return SetError(KMC_B200_ERR_IO, "unable to create " + out_dir.string() + ": " + ec.message());
   kmc_b200_run_stats local{};
@@ -110,34 +157,17 @@ extern "C" int kmc_b200_motion_compensate_run(kmc_b200_handle* h, const char* ru
   // first and last frame: no OxTS packet on one side, copied through byte for byte
   if (int rc = CopyFile(data / (PaddedId(0) + ".bin"), out_dir / (PaddedId(0) + ".bin"))) return rc;
   if (int rc = CopyFile(data / (PaddedId(n - 1) + ".bin"), out_dir / (PaddedId(n - 1) + ".bin"))) return rc;
-  if (n >= 3) {
-    std::vector<double> start, middle, end, oxts_time;
-    if (int rc = LoadTimeStamps(velodyne / "timestamps_start.txt", n, &start)) return rc;
-    if (int rc = LoadTimeStamps(velodyne / "timestamps.txt", n, &middle)) return rc;
-    if (int rc = LoadTimeStamps(velodyne / "timestamps_end.txt", n, &end)) return rc;
-    if (int rc = LoadTimeStamps(run / "oxts" / "timestamps.txt", n, &oxts_time)) return rc;
-    std::vector<double> pose(16 * n);
-    for (size_t i = 0; i < n; ++i)
-      if (int rc = LoadOxtsPose(run / "oxts" / "data" / (PaddedId(i) + ".txt"), &pose[16 * i])) return rc;
-
-    size_t const m = n - 2;
-    std::vector<kmc_b200_frame_params> params(m);
+  local.seconds_prepare = Seconds(t_begin);
+  if (!params.empty()) {
+    size_t const m = params.size();
     std::vector<std::string> in_paths(m), out_paths(m);
     std::vector<const char*> in_c(m), out_c(m);
-    for (size_t i = 1; i + 1 < n; ++i) {
-      double T_start[16], T_end[16];
-      // MakeFrame: the scan's start lies between packets i-1 and i, its end between packets i and i+1
-      int rc = kmc_b200_pose_at_time(oxts_time[i - 1], &pose[16 * (i - 1)], oxts_time[i], &pose[16 * i], start[i], T_start);
-      if (rc == KMC_B200_OK) rc = kmc_b200_pose_at_time(oxts_time[i], &pose[16 * i], oxts_time[i + 1], &pose[16 * (i + 1)], end[i], T_end);
-      if (rc == KMC_B200_OK) rc = kmc_b200_frame_params_from_poses(T_start, T_end, start[i], end[i], middle[i], &params[i - 1]);
-      if (rc != KMC_B200_OK)
-        return SetError(rc, "frame " + std::to_string(i) + ": " + kmc_b200_last_error());
-      in_paths[i - 1] = (data / (PaddedId(i) + ".bin")).string();
-      out_paths[i - 1] = (out_dir / (PaddedId(i) + ".bin")).string();
-      in_c[i - 1] = in_paths[i - 1].c_str();
-      out_c[i - 1] = out_paths[i - 1].c_str();
+    for (size_t k = 0; k < m; ++k) {
+      in_paths[k] = (data / (PaddedId(k + 1) + ".bin")).string();
+      out_paths[k] = (out_dir / (PaddedId(k + 1) + ".bin")).string();
+      in_c[k] = in_paths[k].c_str();
+      out_c[k] = out_paths[k].c_str();
     }
-    local.seconds_prepare = Seconds(t_begin);
     auto const t_pipe = std::chrono::steady_clock::now();
     std::vector<int64_t> points(m);
     if (int rc = kmc_b200_deskew_bin_files(h, static_cast<int32_t>(m), in_c.data(), out_c.data(), params.data(),

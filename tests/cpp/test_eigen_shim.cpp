@@ -94,6 +94,57 @@ TEST(EigenShimTest, AffineFollowsEigenAffineMode) {
   ASSERT_EQ(pose.translation().y(), 5.0);
 }
 
+// The members the reference's camera model uses (camera_model.cpp:9-12, 63-81): dynamic N x 4 / N x 3 matrices,
+// transposes, a fixed-by-dynamic product, the Affine * (4 x N) product, leftCols, Ones and the colwise divide.
+TEST(EigenShimTest, DynamicMatricesOfTheCameraModel) {
+  Eigen::MatrixX4d cloud = Eigen::MatrixX4d::Ones(3, 4);
+  ASSERT_EQ(cloud.rows(), 3);
+  ASSERT_EQ(cloud(2, 3), 1.0);
+  Eigen::MatrixX4d src(3, 4);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) src(r, c) = 10.0 * (r + 1) + c;  // rows (10 11 12 13), (20 ..), (30 ..)
+  cloud.leftCols(3) = static_cast<Eigen::MatrixX4d const&>(src).leftCols(3);
+  ASSERT_EQ(cloud(1, 2), 22.0);
+  ASSERT_EQ(cloud(1, 3), 1.0);            // the homogeneous column is untouched
+  ASSERT_EQ(cloud.data()[1 * 3 + 2], 31.0);  // column-major: column 1, row 2
+
+  Eigen::Matrix4Xd const t{cloud.transpose()};
+  ASSERT_EQ(t.rows(), 4);
+  ASSERT_EQ(t.cols(), 3);
+  ASSERT_EQ(t(2, 1), 22.0);
+  Eigen::MatrixX4d const back{t.transpose()};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) ASSERT_EQ(back(r, c), cloud(r, c));
+
+  // Affine * (4 x N): top rows L p + t w, bottom row passes through
+  Eigen::Affine3d T{Eigen::Affine3d::Identity()};
+  Eigen::Matrix3d L;
+  L << 0, -1, 0, 1, 0, 0, 0, 0, 2;
+  T.linear() = L;
+  T.translation() << 100.0, 200.0, 300.0;
+  Eigen::MatrixX4d const moved{(T * cloud.transpose()).transpose()};
+  ASSERT_EQ(moved(0, 0), -11.0 + 100.0);
+  ASSERT_EQ(moved(0, 1), 10.0 + 200.0);
+  ASSERT_EQ(moved(0, 2), 2.0 * 12.0 + 300.0);
+  ASSERT_EQ(moved(2, 3), 1.0);
+  Eigen::Vector4d const single{T * Eigen::Vector4d{10.0, 11.0, 12.0, 1.0}};
+  for (int c = 0; c < 4; ++c) ASSERT_EQ(moved(0, c), single(c));
+
+  // (3 x 4) * (4 x N), then the perspective divide of every column by the third
+  Eigen::Matrix<double, 3, 4> P;
+  P << 2, 0, 1, 0.5, 0, 3, 1, 0, 0, 0, 1, 0;
+  Eigen::MatrixX3d pixels = (P * cloud.transpose()).transpose();
+  ASSERT_EQ(pixels.rows(), 3);
+  ASSERT_EQ(pixels(1, 0), 2.0 * 20.0 + 22.0 + 0.5);
+  ASSERT_EQ(pixels(1, 1), 3.0 * 21.0 + 22.0);
+  ASSERT_EQ(pixels(1, 2), 22.0);
+  pixels = pixels.array().colwise() / pixels.col(2).array();
+  ASSERT_EQ(pixels(1, 0), (2.0 * 20.0 + 22.0 + 0.5) / 22.0);
+  ASSERT_EQ(pixels(1, 2), 1.0);
+  ASSERT_EQ(pixels.row(2)(1), (3.0 * 31.0 + 32.0) / 32.0);
+  ASSERT_EQ(static_cast<Eigen::MatrixX4d const&>(cloud).row(2)(1), 31.0);
+}
+
 int main(int argc, char** argv) {
   testing::InitGoogleTest(&argc, argv);
   return RUN_ALL_TESTS();

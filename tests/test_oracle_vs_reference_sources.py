@@ -236,3 +236,20 @@ def test_calibration_parsers(tmp_path):
     for k, name in enumerate(("00", "01", "02", "03")):
         assert np.allclose(P[k], np.array(c["P_rect"][name]).reshape(3, 4), rtol=1e-7, atol=0)
     assert np.allclose(S, c["S_rect_00"])
+
+
+def test_log_of_a_slightly_non_orthonormal_pose():
+    """lie::Log(Affine3d) goes through T.rotation() — Eigen's polar factor (lie_algebra.cpp:95).  The oracle restates it as a
+    Jacobi SVD, the Eigen shim under oracle/_ref as a Newton iteration (real Eigen, when present, as JacobiSVD): on poses
+    whose linear block is only approximately a rotation all routes give the same twist, and it is the twist of the nearest
+    rotation (numpy SVD)."""
+    rng = np.random.default_rng(77)
+    for scale in (1e-12, 1e-8, 1e-5):
+        for _ in range(10):
+            T = h.random_pose(rng)
+            T[:3, :3] += rng.normal(0, scale, (3, 3))
+            xi_ref, xi_orc = rb.se3_log(T), ob.se3_log(T)
+            assert np.abs(xi_ref - xi_orc).max() < 1e-11
+            u, _, vt = np.linalg.svd(T[:3, :3])
+            R = u @ np.diag([1, 1, np.sign(np.linalg.det(u @ vt))]) @ vt
+            assert np.abs(xi_ref[3:] - ob.so3_log(R)).max() < 1e-10

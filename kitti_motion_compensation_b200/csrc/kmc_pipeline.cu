@@ -159,6 +159,20 @@ void StagingCopy(void* dst, const void* src, size_t bytes) {
   for (auto& t : pool) t.join();
 }
 
+// Chunk sizes ramp up at the start and down at the end of a transfer.  The first device->host copy cannot start before
+// the first host->device copy and kernel have finished, and while the last results drain nothing flows host->device, so
+// with full-size chunks the link runs in one direction only for two chunk times per call; short first and last chunks
+// shrink that to two short-chunk times.  Below ~4 MB per copy the per-copy latency shows (profiles/r01_e2e_chunk_sweep.log).
+int64_t NextChunkPoints(int64_t chunk_index, int64_t remaining, int64_t capacity) {
+  constexpr int64_t kMinChunk = int64_t{1} << 18;  // 262 144 points = 4 MiB
+  int64_t c = capacity;
+  if (chunk_index < 3) c = std::max(kMinChunk, capacity >> (3 - chunk_index));     // capacity / 8, / 4, / 2, then full
+  if (remaining < 2 * capacity) c = std::min(c, std::max(kMinChunk, remaining / 2));  // halve what is left, down to the floor
+  if (c >= capacity) return std::min(capacity, remaining);
+  if (c >= remaining) return remaining;
+  return std::max<int64_t>(c & ~int64_t{1023}, 1024);  // ramp sizes only: whole multiples of 1024 points
+}
+
 template <class Launch>
 int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
   constexpr int kSlots = kmc_b200_handle::kSlots;
@@ -178,9 +192,10 @@ int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int
   };
 
   int64_t chunk_index = 0;
-  for (int64_t first = 0; first < n; first += h->capacity, ++chunk_index) {
+  int64_t count = 0;
+  for (int64_t first = 0; first < n; first += count, ++chunk_index) {
     int const slot = static_cast<int>(chunk_index % kSlots);
-    int64_t const count = std::min(h->capacity, n - first);
+    count = NextChunkPoints(chunk_index, n - first, h->capacity);
     size_t const bytes = static_cast<size_t>(count) * 16;
     if (int rc = retire(slot)) return rc;
     const float* src = in + 4 * first;

@@ -48,11 +48,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale(LIB_PATH, deps):
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-o", LIB_PATH, *srcs]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+    # every source is an independent translation unit (no -rdc): compile them side by side, then link
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("--shared", "-cudart", "static")]
+    includes = ["-I", os.path.join(REPO_DIR, "include"), "-I", CSRC]
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        cmd = [_nvcc(), *compile_flags, *includes, "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        objs = list(pool.map(compile_one, srcs))
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-o", LIB_PATH, *objs], check=True)
     return LIB_PATH
 
 
@@ -67,7 +81,7 @@ def _cxx() -> str:
 def build_dropin(force: bool = False) -> str:
     """libkitti_motion_compensation_lib.so — the C++ mirror of the reference API (reference CMakeLists.txt:27-29 names
     its library the same), linked against libkmc_b200.so next to it."""
-    build(force=force)
+    build()  # never forced from here: a forced caller has just rebuilt libkmc_b200.so itself
     src = os.path.join(CSRC, "kmc_dropin.cpp")
     inc = os.path.join(REPO_DIR, "include")
     deps = [src, os.path.join(inc, "kmc_b200.h"), os.path.abspath(__file__)]

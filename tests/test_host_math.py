@@ -162,3 +162,36 @@ def test_synth_frame_params_are_deterministic_and_shard_independent(capi):
     assert a[8:].tobytes() == b.tobytes() and np.array_equal(xa[8:], xb)
     assert np.all(xa[:, 0] >= 0) and np.all(xa[:, 0] < 3.0) and np.abs(xa[:, 5]).max() < 0.5
     assert not np.array_equal(xa[0], xa[1])
+
+
+def test_product_host_math_against_the_compiled_reference_sources(capi, oracle):
+    """The product's host doubles (C ABI) against the reference's OWN lie_algebra.cpp / trajectory_interpolation.cpp /
+    data_io.cpp compiled into oracle/_ref — no restatement in between.  Skipped where the library has not been built."""
+    from oracle import ref_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref/libkmc_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(19)
+    for k in range(200):
+        scale = [1.0, 1e-3, 1e-7, 3.0][k % 4]
+        phi = rng.normal(size=3) * scale
+        if np.linalg.norm(phi) > 3.0:
+            phi *= 3.0 / np.linalg.norm(phi)
+        xi = np.concatenate([rng.normal(size=3) * 2, phi])
+        assert np.abs(capi.so3_exp(phi) - rb.so3_exp(phi)).max() < 1e-15
+        assert np.abs(capi.so3_left_jacobian(phi) - rb.left_jacobian(phi)).max() < 1e-14
+        assert np.abs(capi.so3_inverse_left_jacobian(phi) - rb.inverse_left_jacobian(phi)).max() < 1e-12
+        T = rb.se3_exp(xi)
+        assert np.abs(capi.se3_exp(xi) - T).max() < 1e-14
+        assert np.abs(capi.se3_log(T) - rb.se3_log(T)).max() < 1e-11
+    for mercator in (False, True):
+        tol = 1e-8 if mercator else 1e-12
+        for _ in range(20):
+            P1 = helpers.random_pose(rng, mercator)
+            P2 = P1 @ oracle.se3_exp(helpers.random_twist(rng) * rng.uniform(0.1, 6.0))
+            for t in (5.0, 5.1, 5.03, 5.0999):
+                assert np.abs(capi.pose_at_time(5.0, P1, 5.1, P2, t) - rb.pose_at_time(5.0, P1, 5.1, P2, t)).max() < tol
+            got = capi.relative_pose_between_times(5.0, P1, 5.1, P2, 5.05, 5.0123)
+            assert np.abs(got - rb.relative_pose_between_times(5.0, P1, 5.1, P2, 5.05, 5.0123)).max() < tol
+    for _ in range(20):
+        o = [0.0, 49.0 + rng.normal(0, 1), 8.4 + rng.normal(0, 1), 110 + rng.normal(0, 10), *rng.normal(0, 0.1, 2), rng.uniform(-3.1, 3.1)]
+        assert np.abs(capi.oxts_to_pose(*o[1:], 0.8) - rb.oxts_to_pose(o, 0.8)).max() < 2e-9  # translations of ~6e6 m

@@ -75,6 +75,7 @@ __device__ __forceinline__ double Atan2TurnsF64(double y, double x) {
   double q = r * p;
   q = (ay > ax) ? (0.25 - q) : q;
   q = (__double2hiint(x) < 0) ? (0.5 - q) : q;  // sign BIT of x
+  q = (x != x || y != y) ? __longlong_as_double(0x7ff8000000000000ll) : q;  // fmax / fmin drop a NaN operand, atan2 does not
   return copysign(q, y);
 }
 
@@ -112,7 +113,9 @@ __device__ __forceinline__ double FractionOfScanF64(float y, float x) {
   float const c = steep ? 0.25f : (back ? 0.5f : 0.0f);
   float const m = (steep != back) ? -1.0f : 1.0f;
   float const sy = (__float_as_uint(y) >> 31) ? -1.0f : 1.0f;
-  return fma(static_cast<double>(-sy * m), q, static_cast<double>(0.5f - sy * c));
+  // fmaxf / fminf drop a NaN operand; atan2 (and the reference's stamp) does not
+  float const a = (x != x || y != y) ? __int_as_float(0x7fc00000) : 0.5f - sy * c;
+  return fma(static_cast<double>(-sy * m), q, static_cast<double>(a));
 }
 
 // S = sin(s th)/th and C = (1 - cos(s th))/th^2 for x2 = (s th)^2 <= 1, as s*P(x2) and s^2*Q(x2).

@@ -405,6 +405,18 @@ def test_pseudo_time_stamps_device(capi, oracle, cuda):
     torch.cuda.synchronize()
     frac = np.array([oracle.fraction_of_scan_completed(c) for c in cloud[::97]])
     assert np.abs(d_out.cpu().numpy()[::97] - frac).max() < 2e-12
+    # a NaN coordinate gives a NaN stamp, as atan2 does (timestamp_mocking.cpp:46); the neighbours are untouched
+    bad = pts[:8].copy()
+    bad[1, 0] = np.nan
+    bad[4, 1] = np.nan
+    bad[6, 2] = np.nan  # z does not enter the stamp
+    d_bad = dev(torch, bad)
+    d_st = torch.empty(8, dtype=torch.float64, device="cuda")
+    capi.pseudo_time_stamps_device(d_bad.data_ptr(), d_st.data_ptr(), 8, t0, t2, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st = d_st.cpu().numpy()
+    assert np.isnan(st[[1, 4]]).all() and not np.isnan(st[[0, 2, 3, 5, 6, 7]]).any()
+    assert np.array_equal(st[[0, 2, 3, 5, 6, 7]], got[[0, 2, 3, 5, 6, 7]])
     assert got[0] == t0 + 1.0 * (t2 - t0) and got[1] == t0  # frac exactly 1 and 0
 
 

@@ -67,6 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
         objs = list(pool.map(compile_one, srcs))
     subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-o", LIB_PATH, *objs], check=True)
+    shutil.rmtree(obj_dir, ignore_errors=True)  # every build recompiles all sources; the objects need not travel to the GPU box
     return LIB_PATH
 
 

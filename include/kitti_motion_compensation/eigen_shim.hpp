@@ -13,7 +13,9 @@
 #include <cmath>
 #include <cstddef>
 #include <initializer_list>
+#include <memory>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace Eigen {
@@ -242,11 +244,33 @@ using Vector4d = Matrix<double, 4, 1>;
 using Matrix3d = Matrix<double, 3, 3>;
 using Matrix4d = Matrix<double, 4, 4>;
 
+// Storage of the dynamic types: like Eigen, a sized constructor allocates WITHOUT initialising (a 123 397 x 4 result
+// matrix is 4 MB; zero-filling it would cost as much as the deskew call that fills it).
+namespace internal {
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = DefaultInitAllocator<U>;
+  };
+  using std::allocator<T>::allocator;
+  template <class U>
+  void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+    ::new (static_cast<void*>(p)) U;
+  }
+  template <class U, class... Args>
+  void construct(U* p, Args&&... args) {
+    ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+  }
+};
+using Storage = std::vector<double, DefaultInitAllocator<double>>;
+}  // namespace internal
+
 // Dynamic column vector.
 class VectorXd {
  public:
   VectorXd() = default;
-  explicit VectorXd(Index n) : v_(static_cast<size_t>(n), 0.0) {}
+  explicit VectorXd(Index n) : v_(static_cast<size_t>(n)) {}
   Index size() const { return static_cast<Index>(v_.size()); }
   Index rows() const { return size(); }
   Index cols() const { return 1; }
@@ -259,7 +283,7 @@ class VectorXd {
   void resize(Index n) { v_.resize(static_cast<size_t>(n)); }
 
  private:
-  std::vector<double> v_;
+  internal::Storage v_;
 };
 
 template <int R>
@@ -362,7 +386,7 @@ class DynRowsMatrix {
   };
 
   DynRowsMatrix() = default;
-  DynRowsMatrix(Index rows, Index cols) : rows_(rows), v_(static_cast<size_t>(rows * C), 0.0) {
+  DynRowsMatrix(Index rows, Index cols) : rows_(rows), v_(static_cast<size_t>(rows * C)) {
     assert(cols == C);
     (void)cols;
   }
@@ -371,7 +395,11 @@ class DynRowsMatrix {
     std::fill(m.v_.begin(), m.v_.end(), 1.0);
     return m;
   }
-  static DynRowsMatrix Zero(Index rows, Index cols) { return DynRowsMatrix(rows, cols); }
+  static DynRowsMatrix Zero(Index rows, Index cols) {
+    DynRowsMatrix m(rows, cols);
+    std::fill(m.v_.begin(), m.v_.end(), 0.0);
+    return m;
+  }
   Index rows() const { return rows_; }
   Index cols() const { return C; }
   Index size() const { return rows_ * C; }
@@ -394,7 +422,7 @@ class DynRowsMatrix {
 
  private:
   Index rows_ = 0;
-  std::vector<double> v_;
+  internal::Storage v_;
 };
 
 // R x dynamic-columns, COLUMN-major: what `cloud.transpose()` is, so that `T * cloud.transpose()` reads as in the reference.
@@ -402,7 +430,7 @@ template <int R>
 class DynColsMatrix {
  public:
   DynColsMatrix() = default;
-  DynColsMatrix(Index rows, Index cols) : cols_(cols), v_(static_cast<size_t>(R * cols), 0.0) {
+  DynColsMatrix(Index rows, Index cols) : cols_(cols), v_(static_cast<size_t>(R * cols)) {
     assert(rows == R);
     (void)rows;
   }
@@ -419,7 +447,7 @@ class DynColsMatrix {
 
  private:
   Index cols_ = 0;
-  std::vector<double> v_;
+  internal::Storage v_;
 };
 
 template <int C>

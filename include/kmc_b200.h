@@ -170,9 +170,10 @@ KMC_B200_API int kmc_b200_deskew_batch_device(const float* xyzi_in, float* xyzi_
 /* MotionCompensateFrame on the reference's OWN data layout (motion_compensation.cpp:16-28; data_types.hpp:14,58): the
  * cloud and the result are COLUMN-major N x 4 doubles (Eigen::MatrixX4d::data()), stamps is the per-point time vector
  * (LidarScan::timestamps).  The displacement is computed in fp32 and added to the double coordinate, so the result
- * carries no float32 output rounding.  flags_dev (device int, caller-zeroed) receives bit 0 if any stamp lies outside
- * [t_start, t_end] (where the reference asserts) and bit 1 if a 4th-column entry is not the homogeneous 1.  x_req =
- * (t_req - t_start)/(t_end - t_start) must be the value params was built with. */
+ * carries no float32 output rounding.  The 4th column is honoured as the reference does (Affine3d * Vector4d,
+ * motion_compensation.cpp:13): p' = R p + t w, w passed through.  flags_dev (device int, caller-zeroed) receives bit 0 if
+ * any stamp lies outside [t_start, t_end] (where the reference asserts) and bit 1 if a 4th-column entry is not the
+ * homogeneous 1 (informational).  x_req = (t_req - t_start)/(t_end - t_start) must be the value params was built with. */
 KMC_B200_API int kmc_b200_deskew_cloud_f64_device(const double* cloud_colmajor, const double* stamps, double* out_colmajor,
                                                   int64_t n_points, double t_start, double t_end, double t_req,
                                                   const kmc_b200_frame_params* params_host, int* flags_dev, void* stream);
@@ -202,6 +203,13 @@ KMC_B200_API int kmc_b200_deskew_project_frame_device(const float* xyzi_in, floa
 KMC_B200_API int kmc_b200_deskew_project_frame4_device(const float* xyzi_in, float* xyzi_out, float* const uvzc_out[4],
                                                        int64_t n_points, const kmc_b200_frame_params* params_host,
                                                        const kmc_b200_camera_params cameras_host[4], int time_mode, void* stream);
+/* Verification aid for sharded runs ("outputs for G = 8 bit-equal G = 1"): one 64-bit checksum per
+ * frame of a batch stored back to back (frame_offsets_dev as for kmc_b200_deskew_batch_device).  Word j of a frame — the
+ * bit patterns of its floats, counted from the frame's first point — contributes (bits + 0x9E3779B9) * (2 j + 1) mod 2^64;
+ * the checksum is the wrapping sum, so it depends on every bit and position but not on how the work was split.
+ * checksums_dev receives n_frames values (zeroed by the call). */
+KMC_B200_API int kmc_b200_frame_checksums_device(const float* xyzi, const int64_t* frame_offsets_dev, int32_t n_frames,
+                                                 int64_t n_points_total, uint64_t* checksums_dev, void* stream);
 /* Seeded synthetic HDL-64E style scans written straight into device memory (benchmark input):
  * n_scans scans of points_per_scan points, scan k uses seed + first_scan_index + k, so a scan's content does not
  * depend on which GPU generates it.  n_rings x azimuth steps, ring-major, log-uniform range in [2, 120) m. */
@@ -235,9 +243,13 @@ KMC_B200_API int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* xyz
 KMC_B200_API int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_handles, const float* xyzi_in,
                                     float* xyzi_out, const int64_t* frame_offsets, const kmc_b200_frame_params* params,
                                     int32_t n_frames, int time_mode);
-/* The same from host memory (H2D + kernel + D2H on the handle's first stream).  Returns
- * KMC_B200_ERR_TIME_OUT_OF_RANGE when a stamp was outside [t_start, t_end] and KMC_B200_ERR_BAD_SIZE when the 4th
- * column is not all ones (the result is still written); *flags_out (optional) receives the raw bits. */
+/* The same from HOST memory (pageable or pinned), result into host memory.  The double cloud itself never crosses the
+ * link: the handle's host threads round x, y, z to float and form every point's signed trajectory fraction
+ * (t_i - t_start)/(t_end - t_start) - x_req in double; four float columns go up (16 B/point; a fifth only when some
+ * w != 1), three displacement columns come back (12 B/point) and are added to the caller's doubles — bit-identical to
+ * kmc_b200_deskew_cloud_f64_device.  Chunked over the handle's three streams so conversion, copies, kernel and the final
+ * add overlap.  out == cloud (in place) is allowed.  Returns KMC_B200_ERR_TIME_OUT_OF_RANGE when a stamp was outside
+ * [t_start, t_end] (the result is still written); *flags_out (optional) receives the raw bits described above. */
 KMC_B200_API int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud_colmajor, const double* stamps,
                                                 double* out_colmajor, int64_t n_points, double t_start, double t_end, double t_req,
                                                 const kmc_b200_frame_params* params, int* flags_out);

@@ -110,15 +110,22 @@ def build_cpp_test(name: str, force: bool = False) -> str:
     return out
 
 
-def build_example(force: bool = False) -> str:
-    """examples/motion_compensate_runs.cpp -> kitti_motion_compensation_b200/lib/motion_compensate_runs"""
+EXAMPLES = ["motion_compensate_runs", "bench_motion_compensate_frame"]
+
+
+def build_example(force: bool = False, name: str | None = None) -> str:
+    """examples/<name>.cpp -> kitti_motion_compensation_b200/lib/<name> (all of EXAMPLES when name is None; returns the
+    path of motion_compensate_runs, the reference's CLI, in that case)."""
     build_dropin()
-    src = os.path.join(REPO_DIR, "examples", "motion_compensate_runs.cpp")
-    out = os.path.join(LIB_DIR, "motion_compensate_runs")
+    if name is None:
+        paths = [build_example(force, n) for n in EXAMPLES]
+        return paths[0]
+    src = os.path.join(REPO_DIR, "examples", name + ".cpp")
+    out = os.path.join(LIB_DIR, name)
     if not force and not _stale(out, [src, DROPIN_LIB_PATH]):
         return out
     cmd = [_cxx(), "-std=c++17", "-O2", "-Wall", "-I", os.path.join(REPO_DIR, "include"), "-o", out, src,
-           "-L", LIB_DIR, "-lkitti_motion_compensation_lib", "-lkmc_b200", "-Wl,-rpath,$ORIGIN"]
+           "-L", LIB_DIR, "-lkitti_motion_compensation_lib", "-lkmc_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True)
     return out
 

@@ -102,6 +102,7 @@ SIGNATURES = {
                                                         C.POINTER(CameraParams), C.c_int, _vp]),
     "kmc_b200_pseudo_time_stamps_device": (C.c_int, [_vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_pseudo_time_stamps_xy_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
+    "kmc_b200_frame_checksums_device": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, _vp, _vp]),
     "kmc_b200_synth_scans_device": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, _vp]),
     "kmc_b200_synth_frame_params": (C.c_int, [C.c_int32, C.c_uint64, C.c_int64, C.c_double, _vp, _vp]),
     "kmc_b200_handle_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_vp)]),
@@ -289,6 +290,23 @@ def pseudo_time_stamps_device(in_ptr: int, out_ptr: int, n_points: int, start: f
 def synth_scans_device(out_ptr: int, points_per_scan: int, n_scans: int, n_rings: int, seed: int,
                        first_scan_index: int = 0, stream: int = 0) -> None:
     check(lib().kmc_b200_synth_scans_device(out_ptr, points_per_scan, n_scans, n_rings, seed, first_scan_index, stream))
+
+
+def frame_checksums_device(xyzi_ptr: int, offsets_ptr: int, n_frames: int, n_points_total: int, sums_ptr: int, stream: int = 0) -> None:
+    """Per-frame 64-bit position-weighted checksums of a device batch into a device uint64 array (n_frames)."""
+    check(lib().kmc_b200_frame_checksums_device(xyzi_ptr, offsets_ptr, n_frames, n_points_total, sums_ptr, stream))
+
+
+def frame_checksums_numpy(xyzi: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    """The same checksum on the host (definition in include/kmc_b200.h), for tests."""
+    words = np.ascontiguousarray(xyzi, dtype=np.float32).reshape(-1, 4).view(np.uint32).astype(np.uint64)
+    out = np.zeros(len(offsets) - 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for f in range(len(out)):
+            w = words[offsets[f]:offsets[f + 1]].reshape(-1)
+            j = np.arange(w.size, dtype=np.uint64)
+            out[f] = np.sum((w + np.uint64(0x9E3779B9)) * (np.uint64(2) * j + np.uint64(1)), dtype=np.uint64)
+    return out
 
 
 def launch_count() -> int:

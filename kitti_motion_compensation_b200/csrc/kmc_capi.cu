@@ -332,6 +332,19 @@ int kmc_b200_pseudo_time_stamps_xy_device(const double* x, const double* y, doub
   return KMC_B200_OK;
 }
 
+int kmc_b200_frame_checksums_device(const float* xyzi, const int64_t* offsets_dev, int32_t n_frames, int64_t n_total, uint64_t* sums_dev,
+                                    void* stream) {
+  if (n_frames < 0 || n_total < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "frame_checksums_device: negative size");
+  if (n_frames == 0) return KMC_B200_OK;
+  if (!offsets_dev || !sums_dev || (n_total > 0 && !xyzi)) return Fail(KMC_B200_ERR_NULL_POINTER, "frame_checksums_device: null argument");
+  if (!Aligned(xyzi, 16) || !Aligned(offsets_dev, 8) || !Aligned(sums_dev, 8)) return Fail(KMC_B200_ERR_BAD_SIZE, "frame_checksums_device: misaligned buffer");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchFrameChecksums(xyzi, offsets_dev, n_frames, n_total, sums_dev, sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
 int kmc_b200_synth_scans_device(float* out, int64_t points_per_scan, int32_t n_scans, int32_t n_rings, uint64_t seed,
                                 int64_t first_scan_index, void* stream) {
   if (points_per_scan < 0 || n_scans < 0 || n_rings < 2) return Fail(KMC_B200_ERR_BAD_SIZE, "synth_scans_device: bad size");

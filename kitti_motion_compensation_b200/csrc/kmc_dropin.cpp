@@ -21,6 +21,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "kitti_motion_compensation/camera_model.hpp"
@@ -84,6 +85,65 @@ kmc_b200_handle* DefaultHandle() {
   ThrowUnlessOk(kmc_b200_default_handle(g_device.load(), &h), "kmc_b200_default_handle");
   return h;
 }
+
+// The reference's MotionCompensateFrame is re-entrant (it touches only its arguments).  A handle serialises its callers,
+// so concurrent callers each lease their own: the process-wide default handle first, further handles (reference loader
+// capacity, data_io.hpp:17) created on demand and kept for reuse.
+class HandleLease {
+ public:
+  HandleLease() : device_{g_device.load()} {
+    {
+      std::lock_guard<std::mutex> lock(Mu());
+      auto& idle = Idle();
+      for (size_t i = 0; i < idle.size(); ++i) {
+        if (idle[i].first == device_) {
+          handle_ = idle[i].second;
+          idle.erase(idle.begin() + static_cast<std::ptrdiff_t>(i));
+          return;
+        }
+      }
+      if (!DefaultTaken()[device_ & 63]) {
+        DefaultTaken()[device_ & 63] = true;
+        is_default_ = true;
+      }
+    }
+    if (is_default_) {
+      int const rc = kmc_b200_default_handle(device_, &handle_);
+      if (rc != KMC_B200_OK) {
+        std::lock_guard<std::mutex> lock(Mu());
+        DefaultTaken()[device_ & 63] = false;
+      }
+      ThrowUnlessOk(rc, "kmc_b200_default_handle");
+    } else {
+      ThrowUnlessOk(kmc_b200_handle_create(device_, 250000, &handle_), "kmc_b200_handle_create");
+    }
+  }
+  ~HandleLease() {
+    std::lock_guard<std::mutex> lock(Mu());
+    if (is_default_) DefaultTaken()[device_ & 63] = false;
+    else Idle().emplace_back(device_, handle_);
+  }
+  HandleLease(HandleLease const&) = delete;
+  HandleLease& operator=(HandleLease const&) = delete;
+  kmc_b200_handle* get() const { return handle_; }
+
+ private:
+  static std::mutex& Mu() {
+    static std::mutex mu;
+    return mu;
+  }
+  static std::vector<std::pair<int, kmc_b200_handle*>>& Idle() {
+    static auto* idle = new std::vector<std::pair<int, kmc_b200_handle*>>;  // never destroyed: outlives static teardown
+    return *idle;
+  }
+  static bool* DefaultTaken() {
+    static bool taken[64] = {};
+    return taken;
+  }
+  int device_;
+  kmc_b200_handle* handle_ = nullptr;
+  bool is_default_ = false;
+};
 
 }  // namespace
 
@@ -234,10 +294,10 @@ KMC_EXPORT Pointcloud MotionCompensateFrame(Frame const& frame, Time const reque
   if (n == 0) return result;
 
   int flags{0};
-  rc = kmc_b200_deskew_cloud_f64_host(DefaultHandle(), frame.scan.cloud.data(), frame.scan.timestamps.data(), result.data(), n, t1, t2,
+  HandleLease const lease;
+  rc = kmc_b200_deskew_cloud_f64_host(lease.get(), frame.scan.cloud.data(), frame.scan.timestamps.data(), result.data(), n, t1, t2,
                                       requested_time, &params, &flags);
   if (flags & 1) AbortOutOfRange("MotionCompensateFrame (a point stamp)", std::nan(""), t1, t2);  // GetPoseAtTime(point_stamp) asserts
-  if (flags & 2) throw std::invalid_argument("MotionCompensateFrame: the 4th cloud column must be the homogeneous 1 (data_types.hpp:13)");
   ThrowUnlessOk(rc, "kmc_b200_deskew_cloud_f64_host");
   return result;
 }

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "kmc_b200.h"
@@ -36,6 +38,19 @@ int SmCount(int device, int* out);
 
 inline bool ValidMode(int mode) { return mode == KMC_B200_TIME_FROM_AZIMUTH || mode == KMC_B200_TIME_FROM_W; }
 inline bool Aligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// Integer knob from KMC_B200_TUNE="key=value,key=value,..." (experiment switch of the sweep tools), else `fallback`.
+inline int TuneValue(const char* key, int fallback) {
+  const char* env = std::getenv("KMC_B200_TUNE");
+  if (!env) return fallback;
+  size_t const len = std::strlen(key);
+  for (const char* p = env; *p;) {
+    if (std::strncmp(p, key, len) == 0 && p[len] == '=') return std::atoi(p + len + 1);
+    while (*p && *p != ',') ++p;
+    if (*p == ',') ++p;
+  }
+  return fallback;
+}
 
 struct TraceRange {
   explicit TraceRange(const char* name) {

@@ -331,7 +331,8 @@ __global__ void __launch_bounds__(BLOCK)
 // no host-side layout conversion is needed.  The displacement is computed in fp32 from the rounded coordinates and the
 // stamp fraction (formed in double), then added to the DOUBLE coordinate: no float32 output rounding, the result is
 // within ~2.5e-7 of the displacement of the reference's.  72 B/point (32 + 8 read, 32 written), columns coalesced.
-// flags: bit 0 = a stamp outside [t1, t2] (the reference asserts), bit 1 = a 4th-column entry that is not 1.
+// flags: bit 0 = a stamp outside [t1, t2] (the reference asserts), bit 1 = a 4th-column entry that is not 1 (honoured as
+// the reference does: R p + t w, w passed through — motion_compensation.cpp:13).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlockThreads)
     DeskewCloudF64Kernel(const double* __restrict__ cloud, const double* __restrict__ stamps, double* __restrict__ out, int64_t n,
@@ -346,13 +347,50 @@ __global__ void __launch_bounds__(kBlockThreads)
     if (!(t >= t1 && t <= t2)) bad |= 1;
     if (w != 1.0) bad |= 2;
     float const s = static_cast<float>((t - t1) / duration - x_req);  // FractionOfTrajectory, trajectory_interpolation.cpp:49-51
-    float3 const d = DeskewDelta(static_cast<float>(x), static_cast<float>(y), static_cast<float>(z), s, P);
+    float3 const d = DeskewDeltaW(static_cast<float>(x), static_cast<float>(y), static_cast<float>(z), static_cast<float>(w), s, P);
     out[i] = x + static_cast<double>(d.x);
     out[n + i] = y + static_cast<double>(d.y);
     out[2 * n + i] = z + static_cast<double>(d.z);
     out[3 * n + i] = w;
   }
   if (bad) atomicOr(flags, bad);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Narrow transport of the reference-layout HOST path (kmc_b200_deskew_cloud_f64_host).  The link, not the GPU, bounds a
+// host call, so the double cloud never crosses it: the host rounds x, y, z to float, forms each point's signed
+// trajectory fraction s in double and rounds it, and ships four float columns (16 B/point up, a fifth column only when a
+// w != 1 is present); the kernel returns the three displacement columns (12 B/point down) and the host adds them to
+// its own doubles.  Same arithmetic as DeskewCloudF64Kernel operation by operation, hence the same bits.
+// Columns hold stride4 float4s each (chunk length rounded up to 4 points; the pad lanes carry zeros).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDeltaBlockThreads = 128;
+
+template <bool HAS_W>
+__global__ void __launch_bounds__(kDeltaBlockThreads)
+    DeskewDeltaColumnsKernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t stride4,
+                             const __grid_constant__ kmc_b200_frame_params P) {
+  int64_t const step = static_cast<int64_t>(gridDim.x) * kDeltaBlockThreads;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kDeltaBlockThreads + threadIdx.x; i < stride4; i += step) {
+    float4 const x = LoadPoint<0>(in + i), y = LoadPoint<0>(in + stride4 + i), z = LoadPoint<0>(in + 2 * stride4 + i);
+    float4 const s = LoadPoint<0>(in + 3 * stride4 + i);
+    float3 d0, d1, d2, d3;
+    if constexpr (HAS_W) {
+      float4 const w = LoadPoint<0>(in + 4 * stride4 + i);
+      d0 = DeskewDeltaW(x.x, y.x, z.x, w.x, s.x, P);
+      d1 = DeskewDeltaW(x.y, y.y, z.y, w.y, s.y, P);
+      d2 = DeskewDeltaW(x.z, y.z, z.z, w.z, s.z, P);
+      d3 = DeskewDeltaW(x.w, y.w, z.w, w.w, s.w, P);
+    } else {
+      d0 = DeskewDelta(x.x, y.x, z.x, s.x, P);
+      d1 = DeskewDelta(x.y, y.y, z.y, s.y, P);
+      d2 = DeskewDelta(x.z, y.z, z.z, s.z, P);
+      d3 = DeskewDelta(x.w, y.w, z.w, s.w, P);
+    }
+    StorePoint<0>(out + i, make_float4(d0.x, d1.x, d2.x, d3.x));
+    StorePoint<0>(out + stride4 + i, make_float4(d0.y, d1.y, d2.y, d3.y));
+    StorePoint<0>(out + 2 * stride4 + i, make_float4(d0.z, d1.z, d2.z, d3.z));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -430,6 +468,58 @@ __global__ void __launch_bounds__(kBlockThreads)
     sincosf(az, &sa, &ca);
     sincosf(el, &se, &ce);
     out[g] = make_float4(range * ce * ca, range * ce * sa, range * se, inten);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-frame 64-bit checksums of a batch (verification aid: "is the result of a sharded run bit-identical to the unsharded
+// one?" without moving 20 GB).  Word j of a frame (its 4 n_f float bit patterns, j counted from the frame's first point)
+// contributes (bits + 0x9E3779B9) * (2 j + 1) mod 2^64; a frame's checksum is the wrapping sum, so it does not depend on
+// which thread, CTA or GPU added which word, but it does depend on every bit and on every word's position.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kChecksumBlockThreads = 256;
+constexpr int64_t kChecksumItemPoints = 4096;
+
+__global__ void __launch_bounds__(kChecksumBlockThreads)
+    FrameChecksumsKernel(const uint4* __restrict__ points, const int64_t* __restrict__ offsets, int n_frames, int64_t n,
+                         double frames_per_point, unsigned long long* __restrict__ sums) {
+  __shared__ unsigned long long warp_sums[kChecksumBlockThreads / 32];
+  int64_t const n_items = (n + kChecksumItemPoints - 1) / kChecksumItemPoints;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int64_t p0 = item * kChecksumItemPoints;
+    int64_t const p1 = (p0 + kChecksumItemPoints < n) ? (p0 + kChecksumItemPoints) : n;
+    int f = LocateFrame(offsets, n_frames, p0, frames_per_point);
+    while (p0 < p1 && f < n_frames) {
+      int64_t const frame_begin = __ldg(offsets + f);
+      int64_t const frame_end = __ldg(offsets + f + 1);
+      if (frame_end <= p0) {
+        ++f;
+        continue;
+      }
+      int64_t const seg_end = frame_end < p1 ? frame_end : p1;
+      unsigned long long acc = 0;
+      for (int64_t i = p0 + threadIdx.x; i < seg_end; i += kChecksumBlockThreads) {
+        uint4 const v = __ldg(points + i);
+        unsigned long long const j = 4ull * static_cast<unsigned long long>(i - frame_begin);
+        acc += (static_cast<unsigned long long>(v.x) + 0x9E3779B9ull) * (2 * j + 1);
+        acc += (static_cast<unsigned long long>(v.y) + 0x9E3779B9ull) * (2 * j + 3);
+        acc += (static_cast<unsigned long long>(v.z) + 0x9E3779B9ull) * (2 * j + 5);
+        acc += (static_cast<unsigned long long>(v.w) + 0x9E3779B9ull) * (2 * j + 7);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+      if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long total = 0;
+#pragma unroll
+        for (int w = 0; w < kChecksumBlockThreads / 32; ++w) total += warp_sums[w];
+        atomicAdd(sums + f, total);
+      }
+      __syncthreads();
+      p0 = seg_end;
+      ++f;
+    }
   }
 }
 
@@ -781,6 +871,21 @@ cudaError_t LaunchDeskewCloudF64(const double* cloud, const double* stamps, doub
   return cudaGetLastError();
 }
 
+cudaError_t LaunchDeskewDeltaColumns(const float* columns_in, float* columns_out, int64_t stride_points, bool has_w,
+                                     const kmc_b200_frame_params& params, int sm_count, cudaStream_t stream) {
+  if (stride_points <= 0) return cudaSuccess;
+  int64_t const stride4 = stride_points / 4;
+  int64_t grid = (stride4 + kDeltaBlockThreads - 1) / kDeltaBlockThreads;
+  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  if (grid > cap) grid = cap;
+  auto const* in4 = reinterpret_cast<const float4*>(columns_in);
+  auto* out4 = reinterpret_cast<float4*>(columns_out);
+  if (has_w) DeskewDeltaColumnsKernel<true><<<static_cast<unsigned>(grid), kDeltaBlockThreads, 0, stream>>>(in4, out4, stride4, params);
+  else DeskewDeltaColumnsKernel<false><<<static_cast<unsigned>(grid), kDeltaBlockThreads, 0, stream>>>(in4, out4, stride4, params);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
 cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* stamps, int64_t n, double start, double end,
                                      int sm_count, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
@@ -788,6 +893,21 @@ cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* s
   int64_t const cap = static_cast<int64_t>(sm_count) * 8;
   if (grid > cap) grid = cap;
   PseudoTimeStampsXyKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(x, y, stamps, n, start, end - start);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchFrameChecksums(const float* xyzi, const int64_t* offsets_dev, int32_t n_frames, int64_t n_points, uint64_t* sums_dev,
+                                 int sm_count, cudaStream_t stream) {
+  if (n_frames <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(sums_dev, 0, static_cast<size_t>(n_frames) * sizeof(uint64_t), stream);
+  if (e != cudaSuccess || n_points <= 0) return e;
+  int64_t grid = (n_points + kChecksumItemPoints - 1) / kChecksumItemPoints;
+  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  if (grid > cap) grid = cap;
+  FrameChecksumsKernel<<<static_cast<unsigned>(grid), kChecksumBlockThreads, 0, stream>>>(
+      reinterpret_cast<const uint4*>(xyzi), offsets_dev, n_frames, n_points, static_cast<double>(n_frames) / static_cast<double>(n_points),
+      reinterpret_cast<unsigned long long*>(sums_dev));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

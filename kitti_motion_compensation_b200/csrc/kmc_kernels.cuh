@@ -60,8 +60,17 @@ cudaError_t LaunchProject4(const float* in, float* cloud_out, float* const pix_o
 cudaError_t LaunchDeskewCloudF64(const double* cloud, const double* stamps, double* out, int64_t n, double t1, double t2, double x_req,
                                  const kmc_b200_frame_params& params, int* flags_dev, int sm_count, cudaStream_t stream);
 
+// Narrow transport of the reference-layout host path: float columns x | y | z | s [| w] of stride_points entries each
+// (a multiple of 4, 16-byte aligned) -> float columns dx | dy | dz.
+cudaError_t LaunchDeskewDeltaColumns(const float* columns_in, float* columns_out, int64_t stride_points, bool has_w,
+                                     const kmc_b200_frame_params& params, int sm_count, cudaStream_t stream);
+
 cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* stamps, int64_t n, double start, double end,
                                      int sm_count, cudaStream_t stream);
+
+// Position-weighted 64-bit checksum of every frame of a batch (sums_dev: n_frames entries, zeroed by the call).
+cudaError_t LaunchFrameChecksums(const float* xyzi, const int64_t* offsets_dev, int32_t n_frames, int64_t n_points, uint64_t* sums_dev,
+                                 int sm_count, cudaStream_t stream);
 
 cudaError_t LaunchSynthScans(float* out, int64_t points_per_scan, int32_t n_scans, int32_t n_rings, uint64_t seed,
                              int64_t first_scan_index, int sm_count, cudaStream_t stream);

@@ -16,12 +16,14 @@
 #include <cstring>
 #include <deque>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "kmc_b200.h"
+#include "kmc_host_pool.hpp"
 #include "kmc_internal.hpp"
 #include "kmc_kernels.cuh"
 
@@ -30,9 +32,11 @@ namespace {
 using kmc_b200::internal::Aligned;
 using kmc_b200::internal::DeviceGuard;
 using kmc_b200::internal::FailCuda;
+using kmc_b200::internal::HostPool;
 using kmc_b200::internal::kMaxDevices;
 using kmc_b200::internal::SmCount;
 using kmc_b200::internal::TraceRange;
+using kmc_b200::internal::TuneValue;
 using kmc_b200::internal::ValidMode;
 
 int Fail(int status, const std::string& what) { return kmc_b200::internal::SetError(status, what); }
@@ -70,6 +74,12 @@ struct kmc_b200_handle {
   // scratch of the double-precision (reference layout) entry points, grown on demand and kept
   double* d_f64 = nullptr;
   size_t d_f64_bytes = 0;
+  // narrow-transport staging of kmc_b200_deskew_cloud_f64_host: per slot 5 float columns up and 3 down, pinned + device
+  float* f64_pinned = nullptr;
+  float* f64_device = nullptr;
+  int64_t f64_chunk = 0;  // points per column (multiple of 4)
+  // host threads for layout conversion and pageable <-> pinned staging, created on first use
+  std::unique_ptr<kmc_b200::internal::HostPool> pool;
   std::mutex mu;
 };
 
@@ -89,6 +99,8 @@ void FreeHandle(kmc_b200_handle* h) {
   if (h->d_offsets) cudaFree(h->d_offsets);
   if (h->d_params) cudaFree(h->d_params);
   if (h->d_f64) cudaFree(h->d_f64);
+  if (h->f64_pinned) cudaFreeHost(h->f64_pinned);
+  if (h->f64_device) cudaFree(h->f64_device);
   delete h;
 }
 
@@ -137,37 +149,48 @@ int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t
   return rc;
 }
 
+// The handle's host threads: min(8, hardware threads / 2) - 1 workers beside the caller (KMC_B200_TUNE host_threads=N).
+HostPool& Pool(kmc_b200_handle* h) {
+  if (!h->pool) {
+    unsigned const hw = std::max(1u, std::thread::hardware_concurrency());
+    int const dflt = static_cast<int>(std::min(8u, std::max(2u, hw / 2))) - 1;
+    h->pool = std::make_unique<HostPool>(std::min(std::max(TuneValue("host_threads", dflt + 1) - 1, 0), 63));
+  }
+  return *h->pool;
+}
+
 // Pageable caller memory is staged through the handle's pinned slots.  One thread copies about 10-15 GB/s, a quarter of
-// what the PCIe link moves, so chunks of 8 MB and more are split over a few short-lived threads.
-void StagingCopy(void* dst, const void* src, size_t bytes) {
-  constexpr size_t kParallelFrom = size_t{8} << 20;
-  unsigned const hw = std::thread::hardware_concurrency();
-  if (bytes < kParallelFrom || hw < 4) {
+// what the PCIe link moves, so copies of 512 KB and more are cut into 256 KB blocks for the handle's host threads.
+void StagingCopy(kmc_b200_handle* h, void* dst, const void* src, size_t bytes) {
+  constexpr size_t kBlock = size_t{256} << 10;
+  if (bytes < 2 * kBlock) {
     std::memcpy(dst, src, bytes);
     return;
   }
-  size_t const parts = std::min<size_t>({size_t{8}, hw / 2, bytes / (size_t{2} << 20)});
-  size_t const each = ((bytes / parts) + 4095) & ~size_t{4095};
-  std::vector<std::thread> pool;
-  for (size_t k = 1; k < parts; ++k) {
-    size_t const begin = k * each;
-    if (begin >= bytes) break;
-    size_t const len = std::min(each, bytes - begin);
-    pool.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + begin, static_cast<const char*>(src) + begin, len); });
-  }
-  std::memcpy(dst, src, std::min(each, bytes));
-  for (auto& t : pool) t.join();
+  int64_t const blocks = static_cast<int64_t>((bytes + kBlock - 1) / kBlock);
+  Pool(h).Run(blocks, [=](int64_t b) {
+    size_t const begin = static_cast<size_t>(b) * kBlock;
+    std::memcpy(static_cast<char*>(dst) + begin, static_cast<const char*>(src) + begin, std::min(kBlock, bytes - begin));
+  });
 }
 
 // Chunk sizes ramp up at the start and down at the end of a transfer.  The first device->host copy cannot start before
 // the first host->device copy and kernel have finished, and while the last results drain nothing flows host->device, so
 // with full-size chunks the link runs in one direction only for two chunk times per call; short first and last chunks
-// shrink that to two short-chunk times.  Below ~4 MB per copy the per-copy latency shows (profiles/r01_e2e_chunk_sweep.log).
-int64_t NextChunkPoints(int64_t chunk_index, int64_t remaining, int64_t capacity) {
-  constexpr int64_t kMinChunk = int64_t{1} << 18;  // 262 144 points = 4 MiB
+// shrink that to two short-chunk times (profiles/r01_e2e_chunk_sweep.log).  A transfer that fits one slot — a single
+// KITTI scan, the 10 Hz sensor case — is cut into `frame_parts` equal pieces for the same reason: with one piece H2D,
+// kernel and D2H run strictly one after the other (99 us per 130 000-point scan); with four the copies of neighbouring
+// pieces overlap.  Below ~512 KB per copy the per-copy latency dominates.
+int64_t NextChunkPoints(int64_t chunk_index, int64_t remaining, int64_t capacity, int64_t total) {
+  int64_t const min_chunk = std::max(1024, TuneValue("min_chunk", 1 << 15));  // 32 768 points = 512 KiB
+  if (total <= capacity) {
+    int64_t const parts = std::max(1, TuneValue("frame_parts", 4));
+    int64_t const c = std::max(min_chunk, ((total + parts - 1) / parts + 1023) & ~int64_t{1023});
+    return std::min(c, remaining);
+  }
   int64_t c = capacity;
-  if (chunk_index < 3) c = std::max(kMinChunk, capacity >> (3 - chunk_index));     // capacity / 8, / 4, / 2, then full
-  if (remaining < 2 * capacity) c = std::min(c, std::max(kMinChunk, remaining / 2));  // halve what is left, down to the floor
+  if (chunk_index < 3) c = std::max(min_chunk, capacity >> (3 - chunk_index));          // capacity / 8, / 4, / 2, then full
+  if (remaining < 2 * capacity) c = std::min(c, std::max(min_chunk, remaining / 2));  // halve what is left, down to the floor
   if (c >= capacity) return std::min(capacity, remaining);
   if (c >= remaining) return remaining;
   return std::max<int64_t>(c & ~int64_t{1023}, 1024);  // ramp sizes only: whole multiples of 1024 points
@@ -186,7 +209,7 @@ int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int
   auto retire = [&](int slot) -> int {
     if (!pending[slot].active) return KMC_B200_OK;
     KMC_CUDA_TRY(cudaEventSynchronize(h->done[slot]));
-    if (!out_pinned) StagingCopy(out + 4 * pending[slot].first, h->h_out[slot], static_cast<size_t>(pending[slot].count) * 16);
+    if (!out_pinned) StagingCopy(h, out + 4 * pending[slot].first, h->h_out[slot], static_cast<size_t>(pending[slot].count) * 16);
     pending[slot].active = false;
     return KMC_B200_OK;
   };
@@ -195,12 +218,12 @@ int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int
   int64_t count = 0;
   for (int64_t first = 0; first < n; first += count, ++chunk_index) {
     int const slot = static_cast<int>(chunk_index % kSlots);
-    count = NextChunkPoints(chunk_index, n - first, h->capacity);
+    count = NextChunkPoints(chunk_index, n - first, h->capacity, n);
     size_t const bytes = static_cast<size_t>(count) * 16;
     if (int rc = retire(slot)) return rc;
     const float* src = in + 4 * first;
     if (!in_pinned) {
-      StagingCopy(h->h_in[slot], src, bytes);
+      StagingCopy(h, h->h_in[slot], src, bytes);
       src = h->h_in[slot];
     }
     KMC_CUDA_TRY(cudaMemcpyAsync(h->d_in[slot], src, bytes, cudaMemcpyHostToDevice, h->stream[slot]));
@@ -370,6 +393,42 @@ int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_h
   return KMC_B200_OK;
 }
 
+namespace {
+
+// Staging of the narrow transport: three slots of [5 float columns up | 3 float columns down], pinned and on the device.
+int EnsureF64Staging(kmc_b200_handle* h, int64_t chunk_points) {
+  if (chunk_points <= h->f64_chunk) return KMC_B200_OK;
+  if (h->f64_pinned) cudaFreeHost(h->f64_pinned);
+  if (h->f64_device) cudaFree(h->f64_device);
+  h->f64_pinned = nullptr;
+  h->f64_device = nullptr;
+  h->f64_chunk = 0;
+  size_t const bytes = static_cast<size_t>(kmc_b200_handle::kSlots) * 8 * static_cast<size_t>(chunk_points) * sizeof(float);
+  KMC_CUDA_TRY(cudaMallocHost(&h->f64_pinned, bytes));
+  KMC_CUDA_TRY(cudaMalloc(&h->f64_device, bytes));
+  h->f64_chunk = chunk_points;
+  return KMC_B200_OK;
+}
+
+// Points per chunk of a reference-layout host call: a KITTI-size cloud is cut in four so that conversion, both copy
+// directions and the final add overlap; large clouds move in 64 Ki-point chunks (1 MB up, 0.75 MB down).
+int64_t F64ChunkPoints(int64_t n) {
+  int64_t const cap = std::max(4096, TuneValue("f64_chunk", 65536));
+  int64_t const parts = std::max(1, TuneValue("f64_parts", 4));
+  int64_t c = (n + parts - 1) / parts;
+  c = std::min(std::max<int64_t>(c, 8192), cap);
+  return (c + 3) & ~int64_t{3};
+}
+
+}  // namespace
+
+// MotionCompensateFrame on the reference's layout from HOST memory (motion_compensation.cpp:16-28), narrow transport:
+//   pass 1 (host threads)  x, y, z -> float columns, s_i = (t_i - t_start)/(t_end - t_start) - x_req in double -> float column,
+//                          w_i copied through to the result and checked (a float w column is shipped only if some w != 1),
+//                          stamps checked against [t_start, t_end]                       -> pinned staging
+//   H2D 16 B/point -> DeskewDeltaColumnsKernel -> D2H 12 B/point                          (slot's stream)
+//   pass 2 (host threads)  out = x + double(dx), ...                                      <- pinned staging
+// in chunks over three slots, so the host passes of one chunk run while the link and the GPU work on the others.
 int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, const double* stamps, double* out, int64_t n, double t_start,
                                    double t_end, double t_req, const kmc_b200_frame_params* params, int* flags_out) {
   TraceRange const trace("kmc_b200_deskew_cloud_f64_host");
@@ -384,26 +443,103 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
   std::lock_guard<std::mutex> lock(h->mu);
   DeviceGuard const guard(h->device);
   KMC_CUDA_TRY(guard.status());
-  size_t const col = static_cast<size_t>(n) * sizeof(double);
-  if (int rc = EnsureF64Scratch(h, 9 * col + 16)) return rc;
-  double* d = h->d_f64;  // cloud (4 columns) | stamps | result (4 columns) | flags
-  int* d_flags = reinterpret_cast<int*>(d + 9 * n);
-  cudaStream_t const st = h->stream[0];
-  int flags = 0;
-  cudaError_t e = cudaMemcpyAsync(d, cloud, 4 * col, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d + 4 * n, stamps, col, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, sizeof(int), st);
-  if (e == cudaSuccess)
-    e = kmc_b200::dev::LaunchDeskewCloudF64(d, d + 4 * n, d + 5 * n, n, t_start, t_end, (t_req - t_start) / (t_end - t_start), *params, d_flags,
-                                            h->sm_count, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 5 * n, 4 * col, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st);
-  cudaError_t const sync = cudaStreamSynchronize(st);
-  if (e == cudaSuccess) e = sync;
-  if (e != cudaSuccess) return FailCuda(e, "deskew_cloud_f64_host");
-  if (flags_out) *flags_out = flags;
-  if (flags & 1) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "a point stamp lies outside [t_start, t_end] (reference asserts, trajectory_interpolation.cpp:32)");
-  if (flags & 2) return Fail(KMC_B200_ERR_BAD_SIZE, "the 4th cloud column must be the homogeneous 1 (data_types.hpp:13)");
+  constexpr int kSlots = kmc_b200_handle::kSlots;
+  constexpr int64_t kBlock = 4096;  // points per host task
+  int64_t const chunk = F64ChunkPoints(n);
+  if (int rc = EnsureF64Staging(h, chunk)) return rc;
+  HostPool& pool = Pool(h);
+  kmc_b200_frame_params const P = *params;
+  double const duration = t_end - t_start;
+  double const x_req = (t_req - t_start) / duration;
+  const double* const X = cloud;
+  const double* const Y = cloud + n;
+  const double* const Z = cloud + 2 * n;
+  const double* const W = cloud + 3 * n;
+  size_t const slot_floats = 8 * static_cast<size_t>(h->f64_chunk);
+  std::atomic<int> flags{0};
+  struct Pending {
+    int64_t first = 0, count = 0;
+    bool active = false;
+  } pending[kSlots];
+
+  auto retire = [&](int slot) -> int {
+    if (!pending[slot].active) return KMC_B200_OK;
+    KMC_CUDA_TRY(cudaEventSynchronize(h->done[slot]));
+    int64_t const first = pending[slot].first, count = pending[slot].count, stride = (count + 3) & ~int64_t{3};
+    const float* const d = h->f64_pinned + slot * slot_floats + 5 * static_cast<size_t>(h->f64_chunk);
+    pool.Run((count + kBlock - 1) / kBlock, [=](int64_t b) {
+      int64_t const i1 = std::min(count, (b + 1) * kBlock);
+      for (int64_t i = b * kBlock; i < i1; ++i) out[first + i] = X[first + i] + static_cast<double>(d[i]);
+      for (int64_t i = b * kBlock; i < i1; ++i) out[n + first + i] = Y[first + i] + static_cast<double>(d[stride + i]);
+      for (int64_t i = b * kBlock; i < i1; ++i) out[2 * n + first + i] = Z[first + i] + static_cast<double>(d[2 * stride + i]);
+    });
+    pending[slot].active = false;
+    return KMC_B200_OK;
+  };
+
+  auto body = [&]() -> int {
+    int64_t k = 0;
+    for (int64_t first = 0; first < n; first += chunk, ++k) {
+      int const slot = static_cast<int>(k % kSlots);
+      if (int rc = retire(slot)) return rc;
+      int64_t const count = std::min(chunk, n - first), stride = (count + 3) & ~int64_t{3};
+      float* const up = h->f64_pinned + slot * slot_floats;
+      float* const d_up = h->f64_device + slot * slot_floats;
+      float* const d_down = d_up + 5 * static_cast<size_t>(h->f64_chunk);
+      std::atomic<int> chunk_flags{0};
+      pool.Run((count + kBlock - 1) / kBlock, [&, first, count, stride, up](int64_t b) {
+        int64_t const i0 = b * kBlock, i1 = std::min(count, (b + 1) * kBlock);
+        for (int64_t i = i0; i < i1; ++i) up[i] = static_cast<float>(X[first + i]);
+        for (int64_t i = i0; i < i1; ++i) up[stride + i] = static_cast<float>(Y[first + i]);
+        for (int64_t i = i0; i < i1; ++i) up[2 * stride + i] = static_cast<float>(Z[first + i]);
+        int outside = 0, not_one = 0;
+        for (int64_t i = i0; i < i1; ++i) {
+          double const t = stamps[first + i];
+          outside |= !(t >= t_start && t <= t_end);
+          up[3 * stride + i] = static_cast<float>((t - t_start) / duration - x_req);  // FractionOfTrajectory, trajectory_interpolation.cpp:49-51
+        }
+        for (int64_t i = i0; i < i1; ++i) {
+          double const w = W[first + i];
+          not_one |= (w != 1.0);
+          out[3 * n + first + i] = w;
+        }
+        if (i1 == count)
+          for (int c = 0; c < 4; ++c)
+            for (int64_t i = count; i < stride; ++i) up[c * stride + i] = 0.0f;
+        if (outside | not_one) chunk_flags.fetch_or((outside ? 1 : 0) | (not_one ? 2 : 0), std::memory_order_relaxed);
+      });
+      int const cf = chunk_flags.load(std::memory_order_relaxed);
+      flags.fetch_or(cf, std::memory_order_relaxed);
+      bool const has_w = (cf & 2) != 0;
+      if (has_w) {  // rare: a non-homogeneous 4th column travels as a fifth float column
+        pool.Run((stride + kBlock - 1) / kBlock, [=](int64_t b) {
+          int64_t const i1 = std::min(stride, (b + 1) * kBlock);
+          for (int64_t i = b * kBlock; i < i1; ++i) up[4 * stride + i] = i < count ? static_cast<float>(W[first + i]) : 1.0f;
+        });
+      }
+      cudaStream_t const st = h->stream[slot];
+      KMC_CUDA_TRY(cudaMemcpyAsync(d_up, up, static_cast<size_t>(has_w ? 5 : 4) * stride * sizeof(float), cudaMemcpyHostToDevice, st));
+      KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewDeltaColumns(d_up, d_down, stride, has_w, P, h->sm_count, st));
+      KMC_CUDA_TRY(cudaMemcpyAsync(up + 5 * static_cast<size_t>(h->f64_chunk), d_down, static_cast<size_t>(3) * stride * sizeof(float),
+                                   cudaMemcpyDeviceToHost, st));
+      KMC_CUDA_TRY(cudaEventRecord(h->done[slot], st));
+      pending[slot] = {first, count, true};
+    }
+    for (int j = 0; j < kSlots; ++j)
+      if (int rc = retire(static_cast<int>((k + j) % kSlots))) return rc;  // oldest first
+    return KMC_B200_OK;
+  };
+  int const rc = body();
+  if (rc != KMC_B200_OK) {  // no copy may still touch the staging buffers once the call has reported an error
+    std::string const keep = LastError();
+    for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
+    cudaGetLastError();
+    LastError() = keep;
+    return rc;
+  }
+  int const f = flags.load(std::memory_order_relaxed);
+  if (flags_out) *flags_out = f;
+  if (f & 1) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "a point stamp lies outside [t_start, t_end] (reference asserts, trajectory_interpolation.cpp:32)");
   return KMC_B200_OK;
 }
 

@@ -182,6 +182,29 @@ __device__ __forceinline__ float3 DeskewDelta(float x, float y, float z, float s
                      fmaf(C, uz, fmaf(S, vz, s * P.rho_par[2])));
 }
 
+// The same for a homogeneous point (x y z w) with w != 1: the reference applies the correction as an Affine3d times a
+// Vector4d (motion_compensation.cpp:13), i.e. R p + t w with w passed through, so the translation terms scale with w.
+// For w == 1 every operation rounds exactly as in DeskewDelta (w * c == c), so both give the same bits.
+__device__ __forceinline__ float3 DeskewDeltaW(float x, float y, float z, float w, float s, const kmc_b200_frame_params& P) {
+  float const s2 = s * s;
+  float S, C;
+  if (P.wide == 0.0f) {
+    SeriesSC(s, s2, s2 * P.theta2, S, C);
+  } else {
+    HalfAngleSC(s, s2 * P.theta2, S, C);
+  }
+  float const d = fmaf(P.phi[2], z, fmaf(P.phi[1], y, P.phi[0] * x));
+  float const ux = fmaf(P.phi[0], d, fmaf(-P.theta2, x, w * P.phi_x_rho[0]));
+  float const uy = fmaf(P.phi[1], d, fmaf(-P.theta2, y, w * P.phi_x_rho[1]));
+  float const uz = fmaf(P.phi[2], d, fmaf(-P.theta2, z, w * P.phi_x_rho[2]));
+  float const vx = fmaf(P.phi[1], z, fmaf(-P.phi[2], y, w * P.rho_perp[0]));
+  float const vy = fmaf(P.phi[2], x, fmaf(-P.phi[0], z, w * P.rho_perp[1]));
+  float const vz = fmaf(P.phi[0], y, fmaf(-P.phi[1], x, w * P.rho_perp[2]));
+  float const sw = s * w;
+  return make_float3(fmaf(C, ux, fmaf(S, vx, sw * P.rho_par[0])), fmaf(C, uy, fmaf(S, vy, sw * P.rho_par[1])),
+                     fmaf(C, uz, fmaf(S, vz, sw * P.rho_par[2])));
+}
+
 template <int MODE>
 __device__ __forceinline__ float4 DeskewPoint(float4 p, const kmc_b200_frame_params& P) {
   float s;

@@ -91,3 +91,30 @@ def test_missing_library_raises(monkeypatch, capi):
     monkeypatch.setattr(capi, "LIB_PATH", "/nonexistent/libkmc_b200.so")
     with pytest.raises(ImportError, match="no CPU fallback"):
         capi.lib()
+
+
+def test_bench_reference_arm_is_hermetic_and_draws_the_same_twists():
+    """bench.py --impl reference generates its scans and twists with numpy and never imports the CUDA library; its twist
+    generator is the restatement of kmc_b200_synth_frame_params."""
+    import importlib.util
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    from kitti_motion_compensation_b200 import capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for first in (0, 12_345):
+        _, xi = capi.synth_frame_params(50, bench.SEED, first, 0.5)
+        assert np.array_equal(bench.numpy_twists(50, bench.SEED, first), xi)
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--points', '2000'];\n"
+            "try:\n    runpy.run_path('bench.py', run_name='__main__')\nexcept SystemExit:\n    pass\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libkmc_b200' not in maps and 'kitti_motion_compensation_lib' not in maps, 'reference arm mapped the CUDA library'\n"
+            "assert 'kitti_motion_compensation_b200' not in ' '.join(sys.modules), 'reference arm imported the package'\n"
+            "print('hermetic')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "hermetic" in r.stdout, r.stderr[-2000:]
+    assert '"impl": "reference"' in r.stdout

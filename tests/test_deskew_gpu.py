@@ -328,6 +328,36 @@ def test_sharding_is_invisible(capi, oracle, cuda):
         assert np.concatenate(parts).tobytes() == want.tobytes(), f"G={g}"
 
 
+def test_frame_checksums_match_their_definition(capi, oracle, cuda):
+    """kmc_b200_frame_checksums_device: the per-frame 64-bit position-weighted sum of include/kmc_b200.h, on ragged frames
+    (empty, 1 point, frames cut by work items), sensitive to a single flipped bit and to a swap of two points."""
+    torch = cuda
+    sizes = [0, 1, 4095, 4096, 4097, 0, 50_001, 7, 0]
+    pts, offsets, _ = make_batch(oracle, sizes, 4242)
+    d_pts = dev(torch, pts)
+    d_off = dev(torch, offsets)
+    d_sum = torch.empty(len(sizes), dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def sums():
+        capi.frame_checksums_device(d_pts.data_ptr(), d_off.data_ptr(), len(sizes), len(pts), d_sum.data_ptr(), st)
+        torch.cuda.synchronize()
+        return d_sum.cpu().numpy().view(np.uint64).copy()
+
+    base = sums()
+    assert np.array_equal(base, capi.frame_checksums_numpy(pts, offsets))
+    assert np.array_equal(base, sums())  # atomics in any order: the same value every time
+    flipped = pts.copy()
+    flipped.view(np.uint32)[offsets[6] + 12_345, 2] ^= 1
+    d_pts.copy_(torch.from_numpy(flipped))
+    one = sums()
+    assert (one != base).tolist() == [False] * 6 + [True, False, False]
+    swapped = pts.copy()
+    swapped[[offsets[6] + 10, offsets[6] + 11]] = swapped[[offsets[6] + 11, offsets[6] + 10]]
+    d_pts.copy_(torch.from_numpy(swapped))
+    assert sums()[6] != base[6]
+
+
 # ---- host entry points (H2D + kernel + D2H inside the call) ---------------------------------------------------------------
 def test_host_frame_and_batch_calls(capi, oracle, cuda):
     sizes = [130_000, 1, 77_777, 0, 130_000, 250_001]
@@ -686,15 +716,23 @@ def test_reference_layout_f64_entry_point(capi, oracle, cuda):
         print(f"f64 layout: max|dxyz| = {err:.3e} m")
         assert err < 1e-6
         assert np.array_equal(out[:, 3], np.ones(n))
-        # a stamp outside [t_start, t_end] is where the reference asserts; a non-homogeneous 4th column is rejected
+        # a stamp outside [t_start, t_end] is where the reference asserts
         bad = stamps.copy()
         bad[12345] = t2 + 1e-3
         _, flags, rc = h.deskew_cloud_f64(cloud, bad, t0, t2, t1, p)
         assert rc == capi.ERR_TIME_OUT_OF_RANGE and flags & 1
+        # a 4th column that is not the homogeneous 1 is honoured as the reference's Affine3d * Vector4d does: R p + t w
         cloud_w = cloud.copy()
         cloud_w[7, 3] = 2.0
-        _, flags, rc = h.deskew_cloud_f64(cloud_w, stamps, t0, t2, t1, p)
-        assert rc == capi.ERR_BAD_SIZE and flags & 2
+        cloud_w[70_000:70_010, 3] = rng.uniform(-1.0, 3.0, 10)
+        cloud_w[n - 1, 3] = 0.0
+        out_w, flags, rc = h.deskew_cloud_f64(cloud_w, stamps, t0, t2, t1, p)
+        assert rc == capi.OK and flags == 2
+        ref_w = oracle.motion_compensate_frame(cloud_w, stamps, T_start, T_end, t0, t2, t1)
+        assert float(np.abs(out_w[:, :3] - ref_w[:, :3]).max()) < 1e-6
+        assert np.array_equal(out_w[:, 3], cloud_w[:, 3])
+        same = cloud_w[:, 3] == 1.0
+        assert np.array_equal(out_w[same], out[same])  # w == 1 rows: the very same bits as the homogeneous call
         _, _, rc = h.deskew_cloud_f64(cloud, stamps, t0, t2, t2 + 1.0, p)
         assert rc == capi.ERR_TIME_OUT_OF_RANGE
         # empty cloud

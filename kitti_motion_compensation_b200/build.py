@@ -130,7 +130,44 @@ def build_example(force: bool = False, name: str | None = None) -> str:
     return out
 
 
+REFERENCE_DIR = os.environ.get("KMC_REFERENCE_DIR", "/root/reference")
+REFERENCE_TESTS = ["test_motion_compensation", "test_timestamp_mocking", "test_lie_algebra", "test_trajectory_interpolation",
+                   "test_oxts_to_pose"]
+REF_TEST_ROOT = os.path.join(REPO_DIR, "tests", "cpp", "_ref_build")
+
+
+def build_reference_tests(force: bool = False) -> list[str]:
+    """Compiles the reference's OWN gtest files — unmodified, where they lie under /root/reference/test — against this
+    repository's include/ (the drop-in headers) and libkitti_motion_compensation_lib.so, with <gtest/gtest.h> supplied by
+    tests/cpp/gtest_stub (GoogleTest is not in the image).  Binaries go to tests/cpp/_ref_build/build/ and the small run
+    folder the tests open as "../testing_assets/..." is copied beside them (images left out), so that the binaries run on
+    the GPU box, where /root/reference does not exist.  Nothing here is tracked by git.  Returns the binaries that exist."""
+    build_dropin()
+    out_dir = os.path.join(REF_TEST_ROOT, "build")
+    src_dir = os.path.join(REFERENCE_DIR, "test")
+    if os.path.isdir(src_dir):
+        os.makedirs(out_dir, exist_ok=True)
+        assets_src = os.path.join(REFERENCE_DIR, "testing_assets")
+        assets_dst = os.path.join(REF_TEST_ROOT, "testing_assets")
+        if os.path.isdir(assets_src) and (force or not os.path.isdir(assets_dst)):
+            shutil.rmtree(assets_dst, ignore_errors=True)
+            shutil.copytree(assets_src, assets_dst, ignore=shutil.ignore_patterns("image_0*"))
+        tests = os.path.join(REPO_DIR, "tests", "cpp")
+        for name in REFERENCE_TESTS:
+            src, out = os.path.join(src_dir, name + ".cpp"), os.path.join(out_dir, name)
+            if not os.path.exists(src):
+                continue
+            if not force and not _stale(out, [src, os.path.join(tests, "mini_gtest.hpp"), DROPIN_LIB_PATH]):
+                continue
+            cmd = [_cxx(), "-std=c++17", "-O1", "-I", os.path.join(tests, "gtest_stub"), "-I", os.path.join(REPO_DIR, "include"),
+                   "-o", out, src, "-L", LIB_DIR, "-lkitti_motion_compensation_lib", "-lkmc_b200", "-lpthread",
+                   "-Wl,-rpath,$ORIGIN/../../../../kitti_motion_compensation_b200/lib"]
+            subprocess.run(cmd, check=True)
+    return [os.path.join(out_dir, n) for n in REFERENCE_TESTS if os.path.exists(os.path.join(out_dir, n))]
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_dropin(force="--force" in sys.argv))
     print(build_example(force="--force" in sys.argv))
+    print(build_reference_tests(force="--force" in sys.argv))

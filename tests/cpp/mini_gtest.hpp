@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <functional>
 #include <string>
 #include <vector>
@@ -90,7 +91,13 @@ inline int RunAll(const char* filter) {
     if (filter && *filter && t.name.find(filter) == std::string::npos) continue;
     Registry::current_failed() = false;
     std::printf("[ RUN      ] %s\n", t.name.c_str());
-    t.body();
+    try {  // GoogleTest reports an exception escaping SetUp / the body as that test's failure and carries on
+      t.body();
+    } catch (std::exception const& e) {
+      Fail(t.name.c_str(), 0, std::string("C++ exception with description \"") + e.what() + "\" thrown in the test body or SetUp");
+    } catch (...) {
+      Fail(t.name.c_str(), 0, "unknown C++ exception thrown in the test body or SetUp");
+    }
     ++ran;
     if (Registry::current_failed()) {
       ++Registry::failures();

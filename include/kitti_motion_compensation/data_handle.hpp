@@ -18,7 +18,7 @@
 namespace kmc::b200 {
 
 inline void ThrowOnError(int status, const char* what) {
-  if (status != KMC_B200_OK)
+  if (status < 0)  // positive statuses are warnings: the outputs are valid
     throw std::runtime_error(std::string(what) + ": " + kmc_b200_status_string(status) + " — " + kmc_b200_last_error());
 }
 

@@ -19,8 +19,11 @@
  *     16 bytes per point.  Device pointers must be 16-byte aligned.
  *   - Poses are 4x4 doubles, COLUMN-major, i.e. exactly Eigen::Affine3d::matrix().data().
  *   - Times are doubles in seconds (kmc::Time, data_types.hpp:20).
- *   - Every function returns a kmc_b200_status (0 == KMC_B200_OK).  Nothing here aborts or throws; the C++ mirror
- *     re-creates the reference's assert-abort behaviour on top (trajectory_interpolation.cpp:9,32).
+ *   - Every function returns a kmc_b200_status: 0 == KMC_B200_OK, negative = error (nothing usable was produced unless
+ *     the entry point says otherwise), positive = warning (all outputs valid).  Nothing here aborts or throws — C++
+ *     exceptions raised inside the library (std::bad_alloc, thread creation) are caught at the boundary and returned as
+ *     KMC_B200_ERR_INTERNAL; the C++ mirror re-creates the reference's assert-abort behaviour on top
+ *     (trajectory_interpolation.cpp:9,32).
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device entry points are
  *     asynchronous with respect to the host; *_host entry points return after the result is in the caller's memory.
  *   - There is NO CPU fallback: without a usable CUDA device the compute entry points return
@@ -44,6 +47,9 @@ extern "C" {
 #endif
 
 typedef enum kmc_b200_status {
+  /* Positive values are WARNINGS: the call did its work and every output is valid. */
+  KMC_B200_WARN_ACCURACY = 1,           /* per-frame constants built, but the frame moves so fast that max |dxyz| < 1e-5 m is
+                                           not guaranteed for points out to 120 m (see kmc_b200_frame_accuracy_bound) */
   KMC_B200_OK = 0,
   KMC_B200_ERR_NULL_POINTER = -1,
   KMC_B200_ERR_BAD_SIZE = -2,           /* negative n, n_frames, offsets not non-decreasing, misaligned pointer */
@@ -54,7 +60,8 @@ typedef enum kmc_b200_status {
   KMC_B200_ERR_NO_DEVICE = -7,
   KMC_B200_ERR_BAD_MODE = -8,
   KMC_B200_ERR_CAPACITY = -9,           /* scan larger than the handle's capacity */
-  KMC_B200_ERR_IO = -10                 /* file could not be opened / is not a multiple of 16 bytes */
+  KMC_B200_ERR_IO = -10,                /* file could not be opened / is not a multiple of 16 bytes */
+  KMC_B200_ERR_INTERNAL = -11           /* a C++ exception (out of memory, thread creation) was caught at the C boundary */
 } kmc_b200_status;
 
 /* Where a point's position on the trajectory comes from. */
@@ -76,7 +83,21 @@ typedef enum kmc_b200_time_mode {
  *   rho_par[3]  = a (a.rho),        x_req = (t_req - t_start)/(t_end - t_start)   (FROM_W: s = w - x_req)
  *   phi_x_rho[3] = phi x rho,       wide = 1 when theta^2 > KMC_B200_SERIES_THETA2_MAX (kernel then uses the
  *                                   half-angle polynomials valid up to theta = pi), else 0
- * The correction applied to a point p captured at trajectory fraction x is  Exp((x - x_req) xi) p. */
+ * The correction applied to a point p captured at trajectory fraction x is  Exp((x - x_req) xi) p.
+ *
+ * ACCURACY DOMAIN of the fp32 kernels (float4 xyzi in, float4 out).  The displacement delta = Exp(s xi) p - p is computed
+ * in fp32 and added to p once, so against the reference's double result
+ *     |dxyz|  <=  ulp32(|p'|)/2  +  2.5e-7 |delta|  +  5e-8 (|rho| + theta |p|)
+ * (output rounding at the magnitude of the coordinate: 3.8e-6 m for 64-128 m, 7.6e-6 m for 128-256 m; fp32 arithmetic on
+ * the displacement; the azimuth polynomial and the rounding of s).  The 1e-5 m contract therefore holds for |delta| up to
+ * ~20 m per scan with coordinates below 128 m (KITTI's HDL-64E reaches 120 m; a car at 30 m/s turning at 1 rad/s moves a
+ * point at 120 m by 15 m) and for |delta| up to ~6 m with coordinates in 128-256 m; beyond 256 m a float32 coordinate itself cannot hold 1e-5 m.  kmc_b200_frame_accuracy_bound evaluates the
+ * bound for a frame's constants, and kmc_b200_frame_params_from_* return KMC_B200_WARN_ACCURACY (constants still valid)
+ * when the bound at 120 m exceeds 1e-5 m.  The reference-layout entry points (kmc_b200_deskew_cloud_f64_*) add the
+ * displacement to the caller's doubles and have no output-rounding term.
+ * FROM_W mode: w must lie in [0, 1] (the reference asserts on every point stamp, trajectory_interpolation.cpp:32); the
+ * fp32 kernels do not check it — values outside extrapolate the motion, NaN gives NaN — use
+ * kmc_b200_check_fractions_device to validate a buffer, or the f64 entry points, which flag out-of-range stamps. */
 typedef struct kmc_b200_frame_params {
   float phi[3];
   float theta2;
@@ -124,6 +145,11 @@ KMC_B200_API int kmc_b200_frame_params_from_poses(const double T_start_colmajor[
                                      double t_start, double t_end, double t_req, kmc_b200_frame_params* out);
 /* Same from an explicit twist xi = [rho; phi] of the whole scan and the requested fraction x_req in [0,1]. */
 KMC_B200_API int kmc_b200_frame_params_from_twist(const double xi[6], double x_req, kmc_b200_frame_params* out);
+
+/* Upper bound (metres) of max |dxyz| of the fp32 kernels against the reference's double result for a frame with these
+ * constants and points within max_range_m of the sensor (formula above).  Returns KMC_B200_WARN_ACCURACY when the bound
+ * exceeds 1e-5 m, else KMC_B200_OK; *bound_m is written in both cases. */
+KMC_B200_API int kmc_b200_frame_accuracy_bound(const kmc_b200_frame_params* params, double max_range_m, double* bound_m);
 
 /* Lie algebra on the host (lie_algebra.hpp:12-26); 3x3 / 4x4 matrices column-major. */
 KMC_B200_API int kmc_b200_so3_hat(const double phi[3], double out3x3[9]);
@@ -203,6 +229,10 @@ KMC_B200_API int kmc_b200_deskew_project_frame_device(const float* xyzi_in, floa
 KMC_B200_API int kmc_b200_deskew_project_frame4_device(const float* xyzi_in, float* xyzi_out, float* const uvzc_out[4],
                                                        int64_t n_points, const kmc_b200_frame_params* params_host,
                                                        const kmc_b200_camera_params cameras_host[4], int time_mode, void* stream);
+/* Validation pass for KMC_B200_TIME_FROM_W buffers: *flags_dev (device int, zeroed by the call) receives bit 0 if any
+ * point's w lies outside [0, 1] or is NaN — the condition on which the reference asserts for every point stamp
+ * (trajectory_interpolation.cpp:32,47).  Read-only, 16 B/point. */
+KMC_B200_API int kmc_b200_check_fractions_device(const float* xyzi, int64_t n_points, int* flags_dev, void* stream);
 /* Verification aid for sharded runs ("outputs for G = 8 bit-equal G = 1"): one 64-bit checksum per
  * frame of a batch stored back to back (frame_offsets_dev as for kmc_b200_deskew_batch_device).  Word j of a frame — the
  * bit patterns of its floats, counted from the frame's first point — contributes (bits + 0x9E3779B9) * (2 j + 1) mod 2^64;

@@ -25,6 +25,8 @@ ERR_NO_DEVICE = -7
 ERR_BAD_MODE = -8
 ERR_CAPACITY = -9
 ERR_IO = -10
+ERR_INTERNAL = -11
+WARN_ACCURACY = 1  # positive = warning: outputs valid
 
 TIME_FROM_AZIMUTH = 0
 TIME_FROM_W = 1
@@ -76,6 +78,7 @@ SIGNATURES = {
     "kmc_b200_launch_count": (C.c_uint64, []),
     "kmc_b200_frame_params_from_poses": (C.c_int, [_dp, _dp, C.c_double, C.c_double, C.c_double, C.POINTER(FrameParams)]),
     "kmc_b200_frame_params_from_twist": (C.c_int, [_dp, C.c_double, C.POINTER(FrameParams)]),
+    "kmc_b200_frame_accuracy_bound": (C.c_int, [C.POINTER(FrameParams), C.c_double, _dp]),
     "kmc_b200_so3_hat": (C.c_int, [_dp, _dp]),
     "kmc_b200_so3_vee": (C.c_int, [_dp, _dp]),
     "kmc_b200_so3_exp": (C.c_int, [_dp, _dp]),
@@ -102,6 +105,7 @@ SIGNATURES = {
                                                         C.POINTER(CameraParams), C.c_int, _vp]),
     "kmc_b200_pseudo_time_stamps_device": (C.c_int, [_vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_pseudo_time_stamps_xy_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
+    "kmc_b200_check_fractions_device": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
     "kmc_b200_frame_checksums_device": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, _vp, _vp]),
     "kmc_b200_synth_scans_device": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, _vp]),
     "kmc_b200_synth_frame_params": (C.c_int, [C.c_int32, C.c_uint64, C.c_int64, C.c_double, _vp, _vp]),
@@ -148,9 +152,17 @@ def last_error() -> str:
     return lib().kmc_b200_last_error().decode()
 
 
-def check(status: int) -> None:
-    if status != OK:
+last_warning = 0  # the most recent positive (warning) status seen by check()
+
+
+def check(status: int) -> int:
+    """Raises on a negative status; a positive one is a warning (outputs valid) and is returned and remembered."""
+    global last_warning
+    if status < 0:
         raise KmcError(status, last_error() or lib().kmc_b200_status_string(status).decode())
+    if status > 0:
+        last_warning = status
+    return status
 
 
 def _colmajor(m, n) -> np.ndarray:
@@ -176,6 +188,13 @@ def frame_params_from_twist(xi, x_req: float) -> FrameParams:
     v = np.ascontiguousarray(xi, dtype=np.float64)
     check(lib().kmc_b200_frame_params_from_twist(_ptr(v), x_req, C.byref(out)))
     return out
+
+
+def frame_accuracy_bound(params: FrameParams, max_range_m: float = 128.0) -> tuple[float, int]:
+    """(upper bound in metres of max |dxyz| of the fp32 kernels vs the reference for this frame, status OK | WARN_ACCURACY)"""
+    b = C.c_double()
+    rc = check(lib().kmc_b200_frame_accuracy_bound(C.byref(params), max_range_m, C.byref(b)))
+    return b.value, rc
 
 
 def params_array(params) -> np.ndarray:
@@ -290,6 +309,10 @@ def pseudo_time_stamps_device(in_ptr: int, out_ptr: int, n_points: int, start: f
 def synth_scans_device(out_ptr: int, points_per_scan: int, n_scans: int, n_rings: int, seed: int,
                        first_scan_index: int = 0, stream: int = 0) -> None:
     check(lib().kmc_b200_synth_scans_device(out_ptr, points_per_scan, n_scans, n_rings, seed, first_scan_index, stream))
+
+
+def check_fractions_device(xyzi_ptr: int, n_points: int, flags_ptr: int, stream: int = 0) -> None:
+    check(lib().kmc_b200_check_fractions_device(xyzi_ptr, n_points, flags_ptr, stream))
 
 
 def frame_checksums_device(xyzi_ptr: int, offsets_ptr: int, n_frames: int, n_points_total: int, sums_ptr: int, stream: int = 0) -> None:

@@ -99,6 +99,8 @@ const char* kmc_b200_status_string(int status) {
     case KMC_B200_ERR_BAD_MODE: return "unknown time mode";
     case KMC_B200_ERR_CAPACITY: return "handle capacity exceeded";
     case KMC_B200_ERR_IO: return "file I/O error";
+    case KMC_B200_ERR_INTERNAL: return "internal error (C++ exception caught at the C boundary)";
+    case KMC_B200_WARN_ACCURACY: return "warning: frame outside the 1e-5 m accuracy domain of the fp32 kernels";
     default: return "unknown status";
   }
 }
@@ -115,6 +117,37 @@ int kmc_b200_device_count(void) {
 uint64_t kmc_b200_launch_count(void) { return kmc_b200::dev::LaunchCount(); }
 
 // ---- host prep ------------------------------------------------------------------------------------------------
+namespace {
+// include/kmc_b200.h "ACCURACY DOMAIN": ulp32(|p'|)/2 + 2.5e-7 |delta| + 5e-8 (|rho| + theta |p|) at the far end of the range.
+double AccuracyBound(const kmc_b200_frame_params& P, double max_range) {
+  double const theta = std::sqrt(static_cast<double>(P.theta2));
+  double rho2 = 0.0;
+  for (int i = 0; i < 3; ++i) rho2 += static_cast<double>(P.rho_par[i]) * P.rho_par[i] + static_cast<double>(P.rho_perp[i]) * P.rho_perp[i];
+  double const rho = std::sqrt(rho2);
+  double const s_max = std::max(static_cast<double>(P.x_req), 1.0 - static_cast<double>(P.x_req));
+  double const angle = std::min(s_max * theta, M_PI);
+  double const delta = s_max * rho + 2.0 * max_range * std::sin(0.5 * angle);  // translation + chord of the rotation
+  double const reach = max_range + s_max * rho;  // a rotation does not move a point away from the sensor
+  double const half_ulp = std::ldexp(1.0, std::ilogb(std::max(reach, 1e-30)) - 24);
+  return half_ulp + 2.5e-7 * delta + 5e-8 * (rho + theta * max_range);
+}
+constexpr double kContractMetres = 1e-5;  // BASELINE.json north_star
+constexpr double kContractRange = 120.0;  // the HDL-64E's reach; every coordinate then stays below 128 m (3.8e-6 m rounding)
+
+int AccuracyStatus(const kmc_b200_frame_params& P) {
+  if (AccuracyBound(P, kContractRange) <= kContractMetres) return KMC_B200_OK;
+  return Fail(KMC_B200_WARN_ACCURACY, "frame constants are valid, but the motion per scan puts max |dxyz| < 1e-5 m out of reach of the fp32 "
+                                      "kernels for points out to 120 m (kmc_b200_frame_accuracy_bound gives the bound)");
+}
+}  // namespace
+
+int kmc_b200_frame_accuracy_bound(const kmc_b200_frame_params* params, double max_range_m, double* bound_m) {
+  if (!params || !bound_m) return Fail(KMC_B200_ERR_NULL_POINTER, "frame_accuracy_bound: null argument");
+  if (!(max_range_m >= 0.0) || !std::isfinite(max_range_m)) return Fail(KMC_B200_ERR_BAD_SIZE, "frame_accuracy_bound: max_range_m must be finite and >= 0");
+  *bound_m = AccuracyBound(*params, max_range_m);
+  return *bound_m <= kContractMetres ? KMC_B200_OK : KMC_B200_WARN_ACCURACY;
+}
+
 int kmc_b200_frame_params_from_twist(const double xi[6], double x_req, kmc_b200_frame_params* out) {
   if (!xi || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "frame_params_from_twist: null argument");
   for (int i = 0; i < 6; ++i)
@@ -122,7 +155,7 @@ int kmc_b200_frame_params_from_twist(const double xi[6], double x_req, kmc_b200_
   if (!(x_req >= 0.0 && x_req <= 1.0))
     return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "requested fraction outside [0, 1] (reference asserts, trajectory_interpolation.cpp:32)");
   kmc_b200::host::FrameParamsFromTwist(xi, x_req, out);
-  return KMC_B200_OK;
+  return AccuracyStatus(*out);
 }
 
 int kmc_b200_frame_params_from_poses(const double T_start[16], const double T_end[16], double t_start, double t_end,
@@ -135,7 +168,7 @@ int kmc_b200_frame_params_from_poses(const double T_start[16], const double T_en
   if (!kmc_b200::host::RelativeTwist(T_start, T_end, xi))
     return Fail(KMC_B200_ERR_NOT_RIGID, "T_start^-1 T_end has no proper-rotation polar factor");
   kmc_b200::host::FrameParamsFromTwist(xi, (t_req - t_start) / (t_end - t_start), out);
-  return KMC_B200_OK;
+  return AccuracyStatus(*out);
 }
 
 #define KMC_NULLCHECK2(a, b) \
@@ -329,6 +362,17 @@ int kmc_b200_pseudo_time_stamps_xy_device(const double* x, const double* y, doub
   KMC_CUDA_TRY(cudaGetDevice(&device));
   if (int rc = SmCount(device, &sm)) return rc;
   KMC_CUDA_TRY(kmc_b200::dev::LaunchPseudoTimeStampsXy(x, y, stamps, n, start, end, sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
+int kmc_b200_check_fractions_device(const float* xyzi, int64_t n, int* flags_dev, void* stream) {
+  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "check_fractions_device: negative n_points");
+  if (!flags_dev || (n > 0 && !xyzi)) return Fail(KMC_B200_ERR_NULL_POINTER, "check_fractions_device: null argument");
+  if (!Aligned(xyzi, 16) || !Aligned(flags_dev, 4)) return Fail(KMC_B200_ERR_BAD_SIZE, "check_fractions_device: misaligned buffer");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchCheckFractions(xyzi, n, flags_dev, sm, static_cast<cudaStream_t>(stream)));
   return KMC_B200_OK;
 }
 

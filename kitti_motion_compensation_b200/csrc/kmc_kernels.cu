@@ -472,6 +472,22 @@ __global__ void __launch_bounds__(kBlockThreads)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Validation pass for FROM_W buffers: the reference asserts TimeIsInRange for every point stamp
+// (trajectory_interpolation.cpp:32,47); the fp32 deskew kernels do not spend a flag store per launch on it, so callers that
+// cannot vouch for their fractions run this 16 B/point read-only pass first.  Bit 0: some w outside [0, 1] or NaN.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlockThreads)
+    CheckFractionsKernel(const float4* __restrict__ in, int64_t n, int* __restrict__ flags) {
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
+  int bad = 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; i < n; i += stride) {
+    float const w = LoadPoint<0>(in + i).w;
+    bad |= !(w >= 0.0f && w <= 1.0f);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Per-frame 64-bit checksums of a batch (verification aid: "is the result of a sharded run bit-identical to the unsharded
 // one?" without moving 20 GB).  Word j of a frame (its 4 n_f float bit patterns, j counted from the frame's first point)
 // contributes (bits + 0x9E3779B9) * (2 j + 1) mod 2^64; a frame's checksum is the wrapping sum, so it does not depend on
@@ -686,7 +702,7 @@ LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_
   if (cfg.hint < 0 || cfg.hint > 6 || cfg.hint == 2) cfg.hint = 0;  // 3-6: L2 eviction-priority experiments (batch kernel)
   if (cfg.block != 128 && cfg.block != 512) cfg.block = 256;
   if (cfg.ctas_per_sm < 1) cfg.ctas_per_sm = 1;
-  if (cfg.ctas_per_sm > 16) cfg.ctas_per_sm = 16;
+  if (cfg.ctas_per_sm > 4096) cfg.ctas_per_sm = 4096;  // beyond the residency limit the grid stops being persistent (experiment)
   if (cfg.item_tiles < 1) cfg.item_tiles = 1;
   return cfg;
 }
@@ -893,6 +909,17 @@ cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* s
   int64_t const cap = static_cast<int64_t>(sm_count) * 8;
   if (grid > cap) grid = cap;
   PseudoTimeStampsXyKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(x, y, stamps, n, start, end - start);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchCheckFractions(const float* xyzi, int64_t n, int* flags_dev, int sm_count, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(flags_dev, 0, sizeof(int), stream);
+  if (e != cudaSuccess || n <= 0) return e;
+  int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
+  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  if (grid > cap) grid = cap;
+  CheckFractionsKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(reinterpret_cast<const float4*>(xyzi), n, flags_dev);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

@@ -68,6 +68,9 @@ cudaError_t LaunchDeskewDeltaColumns(const float* columns_in, float* columns_out
 cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* stamps, int64_t n, double start, double end,
                                      int sm_count, cudaStream_t stream);
 
+// FROM_W validation: *flags_dev (zeroed by the call) gets bit 0 if any w lies outside [0, 1] or is NaN.
+cudaError_t LaunchCheckFractions(const float* xyzi, int64_t n, int* flags_dev, int sm_count, cudaStream_t stream);
+
 // Position-weighted 64-bit checksum of every frame of a batch (sums_dev: n_frames entries, zeroed by the call).
 cudaError_t LaunchFrameChecksums(const float* xyzi, const int64_t* offsets_dev, int32_t n_frames, int64_t n_points, uint64_t* sums_dev,
                                  int sm_count, cudaStream_t stream);

@@ -78,8 +78,6 @@ struct kmc_b200_handle {
   float* f64_pinned = nullptr;
   float* f64_device = nullptr;
   int64_t f64_chunk = 0;  // points per column (multiple of 4)
-  // host threads for layout conversion and pageable <-> pinned staging, created on first use
-  std::unique_ptr<kmc_b200::internal::HostPool> pool;
   std::mutex mu;
 };
 
@@ -149,26 +147,45 @@ int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t
   return rc;
 }
 
-// The handle's host threads: min(8, hardware threads / 2) - 1 workers beside the caller (KMC_B200_TUNE host_threads=N).
-HostPool& Pool(kmc_b200_handle* h) {
-  if (!h->pool) {
-    unsigned const hw = std::max(1u, std::thread::hardware_concurrency());
-    int const dflt = static_cast<int>(std::min(8u, std::max(2u, hw / 2))) - 1;
-    h->pool = std::make_unique<HostPool>(std::min(std::max(TuneValue("host_threads", dflt + 1) - 1, 0), 63));
+// The library's host threads: ONE pool per process, min(8, hardware threads / 2) - 1 workers beside the calling thread
+// (KMC_B200_TUNE host_threads=N), created on first use and never torn down.  Handles share it and take turns: the host
+// passes of concurrent callers run one after the other at full width while their copies and kernels overlap on the
+// devices — a pool per handle oversubscribes the cores as soon as a few threads call at once (8 callers x 8 threads on a
+// 16-thread box: 3x slower in aggregate than one caller, profiles/r02_sweep_dropin.log).
+class SharedPool {
+ public:
+  template <class F>
+  static void Run(int64_t n_blocks, F&& fn) {
+    SharedPool& self = Instance();
+    std::lock_guard<std::mutex> lock(self.turn_);
+    self.pool_.Run(n_blocks, std::forward<F>(fn));
   }
-  return *h->pool;
-}
+
+ private:
+  static SharedPool& Instance() {
+    static SharedPool* const self = new SharedPool;  // leaked on purpose: worker threads must not be joined during static teardown
+    return *self;
+  }
+  static int Workers() {
+    unsigned const hw = std::max(1u, std::thread::hardware_concurrency());
+    int const dflt = static_cast<int>(std::min(8u, std::max(2u, hw / 2)));
+    return std::min(std::max(TuneValue("host_threads", dflt) - 1, 0), 63);
+  }
+  SharedPool() : pool_(Workers()) {}
+  HostPool pool_;
+  std::mutex turn_;
+};
 
 // Pageable caller memory is staged through the handle's pinned slots.  One thread copies about 10-15 GB/s, a quarter of
 // what the PCIe link moves, so copies of 512 KB and more are cut into 256 KB blocks for the handle's host threads.
-void StagingCopy(kmc_b200_handle* h, void* dst, const void* src, size_t bytes) {
+void StagingCopy(kmc_b200_handle*, void* dst, const void* src, size_t bytes) {
   constexpr size_t kBlock = size_t{256} << 10;
   if (bytes < 2 * kBlock) {
     std::memcpy(dst, src, bytes);
     return;
   }
   int64_t const blocks = static_cast<int64_t>((bytes + kBlock - 1) / kBlock);
-  Pool(h).Run(blocks, [=](int64_t b) {
+  SharedPool::Run(blocks, [=](int64_t b) {
     size_t const begin = static_cast<size_t>(b) * kBlock;
     std::memcpy(static_cast<char*>(dst) + begin, static_cast<const char*>(src) + begin, std::min(kBlock, bytes - begin));
   });
@@ -410,11 +427,13 @@ int EnsureF64Staging(kmc_b200_handle* h, int64_t chunk_points) {
   return KMC_B200_OK;
 }
 
-// Points per chunk of a reference-layout host call: a KITTI-size cloud is cut in four so that conversion, both copy
-// directions and the final add overlap; large clouds move in 64 Ki-point chunks (1 MB up, 0.75 MB down).
+// Points per chunk of a reference-layout host call: a KITTI-size cloud is cut in two so that conversion, both copy
+// directions and the final add overlap (1 / 2 / 3 / 4 / 6 / 8 pieces: 180 / 160 / 189 / 193 / 288 / 304 us per 123 397-point
+// frame, profiles/r02_sweep_dropin.log — every piece costs four API calls and an event wait); large clouds move in
+// 64 Ki-point chunks (1 MB up, 0.75 MB down).
 int64_t F64ChunkPoints(int64_t n) {
   int64_t const cap = std::max(4096, TuneValue("f64_chunk", 65536));
-  int64_t const parts = std::max(1, TuneValue("f64_parts", 4));
+  int64_t const parts = std::max(1, TuneValue("f64_parts", 2));
   int64_t c = (n + parts - 1) / parts;
   c = std::min(std::max<int64_t>(c, 8192), cap);
   return (c + 3) & ~int64_t{3};
@@ -447,7 +466,6 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
   constexpr int64_t kBlock = 4096;  // points per host task
   int64_t const chunk = F64ChunkPoints(n);
   if (int rc = EnsureF64Staging(h, chunk)) return rc;
-  HostPool& pool = Pool(h);
   kmc_b200_frame_params const P = *params;
   double const duration = t_end - t_start;
   double const x_req = (t_req - t_start) / duration;
@@ -467,7 +485,7 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
     KMC_CUDA_TRY(cudaEventSynchronize(h->done[slot]));
     int64_t const first = pending[slot].first, count = pending[slot].count, stride = (count + 3) & ~int64_t{3};
     const float* const d = h->f64_pinned + slot * slot_floats + 5 * static_cast<size_t>(h->f64_chunk);
-    pool.Run((count + kBlock - 1) / kBlock, [=](int64_t b) {
+    SharedPool::Run((count + kBlock - 1) / kBlock, [=](int64_t b) {
       int64_t const i1 = std::min(count, (b + 1) * kBlock);
       for (int64_t i = b * kBlock; i < i1; ++i) out[first + i] = X[first + i] + static_cast<double>(d[i]);
       for (int64_t i = b * kBlock; i < i1; ++i) out[n + first + i] = Y[first + i] + static_cast<double>(d[stride + i]);
@@ -487,7 +505,7 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
       float* const d_up = h->f64_device + slot * slot_floats;
       float* const d_down = d_up + 5 * static_cast<size_t>(h->f64_chunk);
       std::atomic<int> chunk_flags{0};
-      pool.Run((count + kBlock - 1) / kBlock, [&, first, count, stride, up](int64_t b) {
+      SharedPool::Run((count + kBlock - 1) / kBlock, [&, first, count, stride, up](int64_t b) {
         int64_t const i0 = b * kBlock, i1 = std::min(count, (b + 1) * kBlock);
         for (int64_t i = i0; i < i1; ++i) up[i] = static_cast<float>(X[first + i]);
         for (int64_t i = i0; i < i1; ++i) up[stride + i] = static_cast<float>(Y[first + i]);
@@ -512,7 +530,7 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
       flags.fetch_or(cf, std::memory_order_relaxed);
       bool const has_w = (cf & 2) != 0;
       if (has_w) {  // rare: a non-homogeneous 4th column travels as a fifth float column
-        pool.Run((stride + kBlock - 1) / kBlock, [=](int64_t b) {
+        SharedPool::Run((stride + kBlock - 1) / kBlock, [=](int64_t b) {
           int64_t const i1 = std::min(stride, (b + 1) * kBlock);
           for (int64_t i = b * kBlock; i < i1; ++i) up[4 * stride + i] = i < count ? static_cast<float>(W[first + i]) : 1.0f;
         });

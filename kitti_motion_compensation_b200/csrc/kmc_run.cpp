@@ -113,7 +113,7 @@ int PrepareRun(fs::path const& run, size_t* n_out, std::vector<kmc_b200_frame_pa
     int rc = kmc_b200_pose_at_time(oxts_time[i - 1], &pose[16 * (i - 1)], oxts_time[i], &pose[16 * i], start[i], T_start);
     if (rc == KMC_B200_OK) rc = kmc_b200_pose_at_time(oxts_time[i], &pose[16 * i], oxts_time[i + 1], &pose[16 * (i + 1)], end[i], T_end);
     if (rc == KMC_B200_OK) rc = kmc_b200_frame_params_from_poses(T_start, T_end, start[i], end[i], middle[i], &(*params)[i - 1]);
-    if (rc != KMC_B200_OK) return SetError(rc, "frame " + std::to_string(i) + ": " + kmc_b200_last_error());
+    if (rc < 0) return SetError(rc, "frame " + std::to_string(i) + ": " + kmc_b200_last_error());
   }
   return KMC_B200_OK;
 }

@@ -60,7 +60,7 @@ typedef enum kmc_b200_status {
   KMC_B200_ERR_NO_DEVICE = -7,
   KMC_B200_ERR_BAD_MODE = -8,
   KMC_B200_ERR_CAPACITY = -9,           /* scan larger than the handle's capacity */
-  KMC_B200_ERR_IO = -10,                /* file could not be opened / is not a multiple of 16 bytes */
+  KMC_B200_ERR_IO = -10,                /* file could not be opened, read or written / size is not a multiple of 4 bytes */
   KMC_B200_ERR_INTERNAL = -11           /* a C++ exception (out of memory, thread creation) was caught at the C boundary */
 } kmc_b200_status;
 
@@ -189,7 +189,9 @@ KMC_B200_API int kmc_b200_deskew_frame_device(const float* xyzi_in, float* xyzi_
                                  const kmc_b200_frame_params* params_host, int time_mode, void* stream);
 /* A batch of n_frames frames stored back to back.  frame_offsets_dev has n_frames+1 non-decreasing int64 entries
  * (points, not bytes), frame_offsets[0] == 0 and frame_offsets[n_frames] == n_points_total; params_dev has n_frames
- * records.  Both tables live in device memory. */
+ * records.  Both tables live in device memory, so the host cannot verify them: PRECONDITION n_points_total ==
+ * frame_offsets[n_frames] (points beyond the last frame's end are left untouched, the tables are never read out of
+ * bounds). */
 KMC_B200_API int kmc_b200_deskew_batch_device(const float* xyzi_in, float* xyzi_out, const int64_t* frame_offsets_dev,
                                  const kmc_b200_frame_params* params_dev, int32_t n_frames, int64_t n_points_total,
                                  int time_mode, void* stream);
@@ -257,6 +259,12 @@ KMC_B200_API int kmc_b200_handle_destroy(kmc_b200_handle* h);
 /* Process-wide handle of a device, created on first use with the reference loader's capacity (250 000 points) and owned
  * by the library (do not destroy).  Used by the C++ mirror, whose reference signatures carry no handle. */
 KMC_B200_API int kmc_b200_default_handle(int device, kmc_b200_handle** out);
+/* Progress callback of the file pipelines (kmc_b200_deskew_bin_files, kmc_b200_motion_compensate_run): called once per
+ * output file after it has been written, in file order, from the pipeline's retiring thread — the reference prints one
+ * line per frame as its loop advances (handlers.cpp:63).  file_index counts the call's paths (for a run: frame id - 1).
+ * NULL switches it off. */
+typedef void (*kmc_b200_file_done_fn)(int32_t file_index, int64_t n_points, void* user);
+KMC_B200_API int kmc_b200_handle_set_file_callback(kmc_b200_handle* h, kmc_b200_file_done_fn fn, void* user);
 KMC_B200_API int kmc_b200_handle_device(const kmc_b200_handle* h);
 KMC_B200_API int64_t kmc_b200_handle_capacity(const kmc_b200_handle* h);
 
@@ -291,7 +299,9 @@ KMC_B200_API int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const d
 KMC_B200_API int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* xyzi_in, float* uvzc_out, int64_t n_points,
                                              const kmc_b200_camera_params* camera);
 /* KITTI .bin in, deskewed .bin out (KittiPclLoader::LoadPointcloud + MotionCompensateFrame + WritePointcloud,
- * data_io.cpp:101-138, 287-313) without the float->double->float round trip.  n_points_out may be NULL. */
+ * data_io.cpp:101-138, 287-313) without the float->double->float round trip, streamed through the handle's pinned slots
+ * (any file size).  As the reference's loader, a size that is a multiple of 4 bytes is accepted and a trailing partial
+ * point is dropped (data_io.cpp:107-112).  n_points_out may be NULL. */
 KMC_B200_API int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out,
                              const kmc_b200_frame_params* params, int64_t* n_points_out);
 

@@ -112,6 +112,7 @@ SIGNATURES = {
     "kmc_b200_handle_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_vp)]),
     "kmc_b200_handle_destroy": (C.c_int, [_vp]),
     "kmc_b200_default_handle": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "kmc_b200_handle_set_file_callback": (C.c_int, [_vp, _vp, _vp]),
     "kmc_b200_handle_device": (C.c_int, [_vp]),
     "kmc_b200_handle_capacity": (C.c_int64, [_vp]),
     "kmc_b200_deskew_frame_host": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(FrameParams), C.c_int]),

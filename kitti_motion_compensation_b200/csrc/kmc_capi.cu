@@ -7,7 +7,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <mutex>
+#include <new>
 #include <string>
 
 #include "kmc_b200.h"
@@ -33,6 +35,22 @@ int SetError(int status, const std::string& what) {
 int FailCuda(cudaError_t e, const char* where) {
   t_last_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
   return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? KMC_B200_ERR_NO_DEVICE : KMC_B200_ERR_CUDA;
+}
+
+int FailException(const char* where) noexcept {
+  try {
+    try {
+      throw;
+    } catch (std::bad_alloc const&) {
+      t_last_error = std::string(where) + ": out of host memory (std::bad_alloc)";
+    } catch (std::exception const& e) {
+      t_last_error = std::string(where) + ": C++ exception: " + e.what();
+    } catch (...) {
+      t_last_error = std::string(where) + ": unknown C++ exception";
+    }
+  } catch (...) {  // building the message failed as well
+  }
+  return KMC_B200_ERR_INTERNAL;
 }
 
 int SmCount(int device, int* out) {

@@ -365,7 +365,9 @@ KMC_EXPORT std::tuple<Pointcloud, VectorXd> KittiPclLoader::LoadPointcloud(Path 
   std::ifstream in{file, std::ios::in | std::ios::binary | std::ios::ate};
   if (!in.is_open()) throw std::runtime_error("Unable to open requested KITTI pointcloud binary file: " + file.string());
   std::int64_t const bytes{static_cast<std::int64_t>(in.tellg())};
-  if (bytes < 0 || bytes % 16 != 0 || static_cast<size_t>(bytes) > pcl_buffer_size * sizeof(float))
+  // data_io.cpp:107-112: any multiple of 4 bytes is accepted and a trailing partial point is ignored.  The reference would
+  // overrun its 250 000-point buffer on a larger file; that is an error here.
+  if (bytes < 0 || bytes % 4 != 0 || static_cast<size_t>(bytes) > pcl_buffer_size * sizeof(float))
     throw std::runtime_error("Opened KITTI pointcloud binary file is incorrectly formatted: " + file.string());
   in.seekg(0, std::ios::beg);
   in.read(reinterpret_cast<char*>(data_), bytes);
@@ -460,7 +462,12 @@ KMC_EXPORT void MotionCompensateRun(Path const run_folder) {
     run_handle_device = g_device.load();
   }
   kmc_b200_run_stats stats{};
+  // one line per frame as the run advances (handlers.cpp:63); file k of the pipeline is frame k + 1
+  kmc_b200_handle_set_file_callback(
+      run_handle, [](std::int32_t file_index, std::int64_t, void*) { std::cout << "Motion compensated pointcloud number: " << file_index + 1 << std::endl; },
+      nullptr);
   int const rc = kmc_b200_motion_compensate_run(run_handle, run_folder.c_str(), 0, &stats);
+  kmc_b200_handle_set_file_callback(run_handle, nullptr, nullptr);
   if (rc == KMC_B200_ERR_TIME_OUT_OF_RANGE || rc == KMC_B200_ERR_EMPTY_INTERVAL) {
     std::fprintf(stderr, "MotionCompensateRun: %s (the reference asserts here: trajectory_interpolation.cpp:32)\n", kmc_b200_last_error());
     std::abort();
@@ -470,8 +477,6 @@ KMC_EXPORT void MotionCompensateRun(Path const run_folder) {
     std::exit(0);  // the reference's convention for an unreadable time-stamp file (data_io.cpp:27-30)
   }
   ThrowUnlessOk(rc, "kmc_b200_motion_compensate_run");
-  for (std::int64_t i{1}; i + 1 < stats.frames; ++i) std::cout << "Motion compensated pointcloud number: " << i << '\n';
-  std::cout << std::flush;
 }
 
 // ---- calibration files + projection (camera_model.cpp, data_io.cpp:168-210,321-406) -----------------------------------------

@@ -31,6 +31,10 @@ int SetError(int status, const std::string& what);
 // Records the CUDA error (name + text, prefixed by `where`) and maps it to KMC_B200_ERR_NO_DEVICE / KMC_B200_ERR_CUDA.
 int FailCuda(cudaError_t e, const char* where);
 
+// Inside a catch (...) at the C boundary: records what was caught and returns KMC_B200_ERR_INTERNAL.  No exception may
+// cross an extern "C" function (std::bad_alloc from a staging vector, std::system_error from thread creation ...).
+int FailException(const char* where) noexcept;
+
 constexpr int kMaxDevices = 64;  // device ordinals the per-device tables cover
 
 // Multiprocessor count of `device`, cached.
@@ -91,6 +95,10 @@ class DeviceGuard {
 };
 
 }  // namespace kmc_b200::internal
+
+// Closes a function-try-block of an extern "C" entry point:  int kmc_b200_x(...) try { ... } KMC_CATCH_AT_BOUNDARY("x")
+#define KMC_CATCH_AT_BOUNDARY(name) \
+  catch (...) { return ::kmc_b200::internal::FailException(name); }
 
 #define KMC_CUDA_TRY(expr)                                                      \
   do {                                                                          \

@@ -198,7 +198,9 @@ __global__ void __launch_bounds__(BLOCK)
     int64_t const p1 = (p0 + item_points < n) ? (p0 + item_points) : n;
     // in/out address the chunk [point_base, point_base + n) of the batch; offsets count from the start of the batch
     int f = LocateFrame(offsets, n_frames, p0 + point_base, frames_per_point);
-    while (p0 < p1) {
+    // f < n_frames: a caller whose n exceeds offsets[n_frames] (a broken precondition, the tables live on the device and
+    // cannot be checked by the host) leaves the surplus points untouched instead of walking off the tables
+    while (p0 < p1 && f < n_frames) {
       int64_t const frame_end = __ldg(offsets + f + 1) - point_base;
       if (frame_end <= p0) {  // empty frame
         ++f;

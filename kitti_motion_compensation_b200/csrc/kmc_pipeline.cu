@@ -78,6 +78,9 @@ struct kmc_b200_handle {
   float* f64_pinned = nullptr;
   float* f64_device = nullptr;
   int64_t f64_chunk = 0;  // points per column (multiple of 4)
+  // kmc_b200_handle_set_file_callback: called after every output file of kmc_b200_deskew_bin_files has been written
+  kmc_b200_file_done_fn file_done = nullptr;
+  void* file_done_user = nullptr;
   std::mutex mu;
 };
 
@@ -127,17 +130,20 @@ int EnsureTables(kmc_b200_handle* h, int64_t n_frames) {
   return KMC_B200_OK;
 }
 
-// Streams a host array through the device in capacity-sized chunks: stage (if pageable) -> H2D -> kernel -> D2H ->
-// unstage, three slots deep so the copy engines and the SMs overlap.  `launch(slot, chunk_first_point, chunk_points)`
-// enqueues the kernel for a chunk on h->stream[slot].
-template <class Launch>
-int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch);
+// Core of every host pipeline: chunks of the point range [0, n) rotate through the handle's three stream / buffer slots
+//   fetch(slot, first, count) -> pinned source of the chunk (the caller's pinned memory, or h_in[slot] after a staging
+//                                copy or a pread)                                                        [host, this thread]
+//   H2D -> launch(slot, first, count) -> D2H into sink(slot, first) (caller's pinned memory or h_out[slot])   [slot's stream]
+//   deliver(slot, first, count) once the chunk's event has fired (unstage / pwrite; nothing for pinned)  [host, this thread]
+// so the copy engines, the SMs and the host work of neighbouring chunks overlap.
+template <class Fetch, class Launch, class Sink, class Deliver>
+int StreamChunksImpl(kmc_b200_handle* h, int64_t n, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver);
 
 // On any failure the slots' streams are drained before returning, so that no copy is still reading or writing the
 // caller's buffers after the call has reported an error.
-template <class Launch>
-int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
-  int const rc = StreamThroughDeviceImpl(h, in, out, n, launch);
+template <class Fetch, class Launch, class Sink, class Deliver>
+int StreamChunks(kmc_b200_handle* h, int64_t n, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver) {
+  int const rc = StreamChunksImpl(h, n, fetch, launch, sink, deliver);
   if (rc != KMC_B200_OK) {
     std::string const keep = LastError();
     for (int s = 0; s < kmc_b200_handle::kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
@@ -213,11 +219,9 @@ int64_t NextChunkPoints(int64_t chunk_index, int64_t remaining, int64_t capacity
   return std::max<int64_t>(c & ~int64_t{1023}, 1024);  // ramp sizes only: whole multiples of 1024 points
 }
 
-template <class Launch>
-int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
+template <class Fetch, class Launch, class Sink, class Deliver>
+int StreamChunksImpl(kmc_b200_handle* h, int64_t n, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver) {
   constexpr int kSlots = kmc_b200_handle::kSlots;
-  bool const in_pinned = IsPinnedHost(in);
-  bool const out_pinned = IsPinnedHost(out);
   struct Pending {
     int64_t first = 0, count = 0;
     bool active = false;
@@ -226,9 +230,8 @@ int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int
   auto retire = [&](int slot) -> int {
     if (!pending[slot].active) return KMC_B200_OK;
     KMC_CUDA_TRY(cudaEventSynchronize(h->done[slot]));
-    if (!out_pinned) StagingCopy(h, out + 4 * pending[slot].first, h->h_out[slot], static_cast<size_t>(pending[slot].count) * 16);
     pending[slot].active = false;
-    return KMC_B200_OK;
+    return deliver(slot, pending[slot].first, pending[slot].count);
   };
 
   int64_t chunk_index = 0;
@@ -238,15 +241,11 @@ int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int
     count = NextChunkPoints(chunk_index, n - first, h->capacity, n);
     size_t const bytes = static_cast<size_t>(count) * 16;
     if (int rc = retire(slot)) return rc;
-    const float* src = in + 4 * first;
-    if (!in_pinned) {
-      StagingCopy(h, h->h_in[slot], src, bytes);
-      src = h->h_in[slot];
-    }
+    const float* src = nullptr;
+    if (int rc = fetch(slot, first, count, &src)) return rc;
     KMC_CUDA_TRY(cudaMemcpyAsync(h->d_in[slot], src, bytes, cudaMemcpyHostToDevice, h->stream[slot]));
     if (int rc = launch(slot, first, count)) return rc;
-    float* dst = out_pinned ? out + 4 * first : h->h_out[slot];
-    KMC_CUDA_TRY(cudaMemcpyAsync(dst, h->d_out[slot], bytes, cudaMemcpyDeviceToHost, h->stream[slot]));
+    KMC_CUDA_TRY(cudaMemcpyAsync(sink(slot, first), h->d_out[slot], bytes, cudaMemcpyDeviceToHost, h->stream[slot]));
     KMC_CUDA_TRY(cudaEventRecord(h->done[slot], h->stream[slot]));
     pending[slot] = {first, count, true};
   }
@@ -255,6 +254,28 @@ int StreamThroughDeviceImpl(kmc_b200_handle* h, const float* in, float* out, int
     if (int rc = retire(slot)) return rc;
   }
   return KMC_B200_OK;
+}
+
+// A host ARRAY through the device: pinned caller memory is copied directly, pageable memory is staged through the slots.
+template <class Launch>
+int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
+  bool const in_pinned = IsPinnedHost(in);
+  bool const out_pinned = IsPinnedHost(out);
+  return StreamChunks(
+      h, n,
+      [&](int slot, int64_t first, int64_t count, const float** src) -> int {
+        *src = in + 4 * first;
+        if (!in_pinned) {
+          StagingCopy(h, h->h_in[slot], in + 4 * first, static_cast<size_t>(count) * 16);
+          *src = h->h_in[slot];
+        }
+        return KMC_B200_OK;
+      },
+      launch, [&](int slot, int64_t first) -> float* { return out_pinned ? out + 4 * first : h->h_out[slot]; },
+      [&](int slot, int64_t first, int64_t count) -> int {
+        if (!out_pinned) StagingCopy(h, out + 4 * first, h->h_out[slot], static_cast<size_t>(count) * 16);
+        return KMC_B200_OK;
+      });
 }
 
 int CheckOffsets(const int64_t* offsets, int32_t n_frames) {
@@ -272,7 +293,7 @@ int CheckOffsets(const int64_t* offsets, int32_t n_frames) {
 extern "C" {
 
 // ---- handle ---------------------------------------------------------------------------------------------------------
-int kmc_b200_handle_create(int device, int64_t capacity_points, kmc_b200_handle** out) {
+int kmc_b200_handle_create(int device, int64_t capacity_points, kmc_b200_handle** out) try {
   if (!out) return Fail(KMC_B200_ERR_NULL_POINTER, "handle_create: null output");
   *out = nullptr;
   if (capacity_points <= 0) return Fail(KMC_B200_ERR_BAD_SIZE, "handle_create: capacity must be positive");
@@ -302,13 +323,14 @@ int kmc_b200_handle_create(int device, int64_t capacity_points, kmc_b200_handle*
   *out = h;
   return KMC_B200_OK;
 }
+KMC_CATCH_AT_BOUNDARY("handle_create")
 
 int kmc_b200_handle_destroy(kmc_b200_handle* h) {
   FreeHandle(h);
   return KMC_B200_OK;
 }
 
-int kmc_b200_default_handle(int device, kmc_b200_handle** out) {
+int kmc_b200_default_handle(int device, kmc_b200_handle** out) try {
   if (!out) return Fail(KMC_B200_ERR_NULL_POINTER, "default_handle: null output");
   *out = nullptr;
   if (device < 0 || device >= kMaxDevices) return Fail(KMC_B200_ERR_NO_DEVICE, "default_handle: device ordinal out of range");
@@ -321,13 +343,22 @@ int kmc_b200_default_handle(int device, kmc_b200_handle** out) {
   *out = table[device];
   return KMC_B200_OK;
 }
+KMC_CATCH_AT_BOUNDARY("default_handle")
+
+int kmc_b200_handle_set_file_callback(kmc_b200_handle* h, kmc_b200_file_done_fn fn, void* user) {
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "handle_set_file_callback: null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->file_done = fn;
+  h->file_done_user = user;
+  return KMC_B200_OK;
+}
 
 int kmc_b200_handle_device(const kmc_b200_handle* h) { return h ? h->device : KMC_B200_ERR_NULL_POINTER; }
 int64_t kmc_b200_handle_capacity(const kmc_b200_handle* h) { return h ? h->capacity : KMC_B200_ERR_NULL_POINTER; }
 
 // ---- host entry points -------------------------------------------------------------------------------------------------
 int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, int64_t n, const kmc_b200_frame_params* params,
-                               int mode) {
+                               int mode) try {
   TraceRange const trace("kmc_b200_deskew_frame_host");
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_frame_host: null handle");
   if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_frame_host: negative n_points");
@@ -345,9 +376,10 @@ int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, 
     return KMC_B200_OK;
   });
 }
+KMC_CATCH_AT_BOUNDARY("deskew_frame_host")
 
 int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* in, float* out, const int64_t* offsets,
-                               const kmc_b200_frame_params* params, int32_t n_frames, int mode) {
+                               const kmc_b200_frame_params* params, int32_t n_frames, int mode) try {
   TraceRange const trace("kmc_b200_deskew_batch_host");
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_host: null handle");
   if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_host: negative n_frames");
@@ -373,9 +405,10 @@ int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* in, float* out, 
     return KMC_B200_OK;
   });
 }
+KMC_CATCH_AT_BOUNDARY("deskew_batch_host")
 
 int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_handles, const float* in, float* out,
-                                    const int64_t* offsets, const kmc_b200_frame_params* params, int32_t n_frames, int mode) {
+                                    const int64_t* offsets, const kmc_b200_frame_params* params, int32_t n_frames, int mode) try {
   TraceRange const trace("kmc_b200_deskew_batch_multi_gpu");
   if (!handles || n_handles <= 0) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_batch_multi_gpu: no handles");
   if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_batch_multi_gpu: negative n_frames");
@@ -392,15 +425,27 @@ int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_h
   std::vector<int> status(static_cast<size_t>(n_handles), KMC_B200_OK);
   std::vector<std::string> message(static_cast<size_t>(n_handles));
   std::vector<std::thread> workers;
+  struct JoinAll {
+    std::vector<std::thread>& pool;
+    ~JoinAll() {
+      for (auto& w : pool)
+        if (w.joinable()) w.join();
+    }
+  } join_all{workers};
+  workers.reserve(static_cast<size_t>(n_handles));
   for (int32_t i = 0; i < n_handles; ++i) {
     workers.emplace_back([&, i] {
-      int64_t fb = 0, fe = 0;
-      kmc_b200_shard_range(n_frames, n_handles, i, &fb, &fe);
-      if (fe <= fb) return;
-      std::vector<int64_t> local(static_cast<size_t>(fe - fb + 1));
-      for (int64_t f = fb; f <= fe; ++f) local[static_cast<size_t>(f - fb)] = offsets[f] - offsets[fb];
-      status[i] = kmc_b200_deskew_batch_host(handles[i], in ? in + 4 * offsets[fb] : nullptr, out ? out + 4 * offsets[fb] : nullptr,
-                                             local.data(), params + fb, static_cast<int32_t>(fe - fb), mode);
+      try {
+        int64_t fb = 0, fe = 0;
+        kmc_b200_shard_range(n_frames, n_handles, i, &fb, &fe);
+        if (fe <= fb) return;
+        std::vector<int64_t> local(static_cast<size_t>(fe - fb + 1));
+        for (int64_t f = fb; f <= fe; ++f) local[static_cast<size_t>(f - fb)] = offsets[f] - offsets[fb];
+        status[i] = kmc_b200_deskew_batch_host(handles[i], in ? in + 4 * offsets[fb] : nullptr, out ? out + 4 * offsets[fb] : nullptr,
+                                               local.data(), params + fb, static_cast<int32_t>(fe - fb), mode);
+      } catch (...) {
+        status[i] = kmc_b200::internal::FailException("deskew_batch_multi_gpu (device thread)");
+      }
       if (status[i] != KMC_B200_OK) message[i] = LastError();
     });
   }
@@ -409,6 +454,7 @@ int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles, int32_t n_h
     if (status[i] != KMC_B200_OK) return Fail(status[i], "device " + std::to_string(handles[i]->device) + ": " + message[i]);
   return KMC_B200_OK;
 }
+KMC_CATCH_AT_BOUNDARY("deskew_batch_multi_gpu")
 
 namespace {
 
@@ -449,7 +495,7 @@ int64_t F64ChunkPoints(int64_t n) {
 //   pass 2 (host threads)  out = x + double(dx), ...                                      <- pinned staging
 // in chunks over three slots, so the host passes of one chunk run while the link and the GPU work on the others.
 int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, const double* stamps, double* out, int64_t n, double t_start,
-                                   double t_end, double t_req, const kmc_b200_frame_params* params, int* flags_out) {
+                                   double t_end, double t_req, const kmc_b200_frame_params* params, int* flags_out) try {
   TraceRange const trace("kmc_b200_deskew_cloud_f64_host");
   if (flags_out) *flags_out = 0;
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null handle");
@@ -560,9 +606,10 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
   if (f & 1) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "a point stamp lies outside [t_start, t_end] (reference asserts, trajectory_interpolation.cpp:32)");
   return KMC_B200_OK;
 }
+KMC_CATCH_AT_BOUNDARY("deskew_cloud_f64_host")
 
 int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n, double start, double end,
-                                        double* stamps) {
+                                        double* stamps) try {
   TraceRange const trace("kmc_b200_pseudo_time_stamps_xy_host");
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "pseudo_time_stamps_xy_host: null handle");
   if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "pseudo_time_stamps_xy_host: negative n_points");
@@ -583,8 +630,9 @@ int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, con
   if (e != cudaSuccess) return FailCuda(e, "pseudo_time_stamps_xy_host");
   return KMC_B200_OK;
 }
+KMC_CATCH_AT_BOUNDARY("pseudo_time_stamps_xy_host")
 
-int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* in, float* uvzc_out, int64_t n, const kmc_b200_camera_params* camera) {
+int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* in, float* uvzc_out, int64_t n, const kmc_b200_camera_params* camera) try {
   TraceRange const trace("kmc_b200_project_frame_host");
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "project_frame_host: null handle");
   if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "project_frame_host: negative n_points");
@@ -602,37 +650,12 @@ int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* in, float* uvzc
     return KMC_B200_OK;
   });
 }
+KMC_CATCH_AT_BOUNDARY("project_frame_host")
 
-int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out, const kmc_b200_frame_params* params,
-                             int64_t* n_points_out) {
-  TraceRange const trace("kmc_b200_deskew_bin_file");
-  if (!h || !path_in || !path_out || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_file: null argument");
-  FILE* f = std::fopen(path_in, "rb");
-  if (!f) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path_in);
-  std::fseek(f, 0, SEEK_END);
-  long const size = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
-  if (size < 0 || size % 16 != 0) {
-    std::fclose(f);
-    return Fail(KMC_B200_ERR_IO, std::string("KITTI pointcloud binary file is not a whole number of xyzi points: ") + path_in);
-  }
-  int64_t const n = size / 16;
-  std::vector<float> buf(static_cast<size_t>(4 * n)), res(static_cast<size_t>(4 * n));
-  size_t const got = n ? std::fread(buf.data(), 16, static_cast<size_t>(n), f) : 0;
-  std::fclose(f);
-  if (static_cast<int64_t>(got) != n) return Fail(KMC_B200_ERR_IO, std::string("short read: ") + path_in);
-  if (int rc = kmc_b200_deskew_frame_host(h, buf.data(), res.data(), n, params, KMC_B200_TIME_FROM_AZIMUTH)) return rc;
-  FILE* g = std::fopen(path_out, "wb");
-  if (!g) return Fail(KMC_B200_ERR_IO, std::string("unable to create output file: ") + path_out);
-  size_t const put = n ? std::fwrite(res.data(), 16, static_cast<size_t>(n), g) : 0;
-  bool const closed = (std::fclose(g) == 0);
-  if (static_cast<int64_t>(put) != n || !closed) return Fail(KMC_B200_ERR_IO, std::string("short write: ") + path_out);
-  if (n_points_out) *n_points_out = n;
-  return KMC_B200_OK;
-}
 
 
 // ---- many KITTI .bin files through one overlapped pipeline ------------------------------------------------------------------
+extern "C++" {  // templates below: no C linkage inside the extern "C" region
 namespace {
 
 // Runs fn(0..n_items-1) on up to n_threads short-lived host threads; returns the first non-zero status.
@@ -661,6 +684,14 @@ int ParallelFor(int64_t n_items, int n_threads, const std::function<int(int64_t)
     body();
   } else {
     std::vector<std::thread> pool;
+    struct JoinAll {
+      std::vector<std::thread>& pool;
+      ~JoinAll() {
+        for (auto& th : pool)
+          if (th.joinable()) th.join();
+      }
+    } join_all{pool};
+    pool.reserve(static_cast<size_t>(n_threads));
     for (int t = 0; t < n_threads; ++t) pool.emplace_back(body);
     for (auto& th : pool) th.join();
   }
@@ -668,37 +699,117 @@ int ParallelFor(int64_t n_items, int n_threads, const std::function<int(int64_t)
   return status.load();
 }
 
-int ReadWholeFile(const char* path, void* dst, size_t bytes) {
-  int const fd = ::open(path, O_RDONLY | O_CLOEXEC);
-  if (fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path);
+// pread / pwrite of a byte range, restarted on EINTR and short transfers.
+bool ReadRange(int fd, void* dst, size_t bytes, off_t offset) {
   size_t done = 0;
   while (done < bytes) {
-    ssize_t const got = ::pread(fd, static_cast<char*>(dst) + done, bytes - done, static_cast<off_t>(done));
+    ssize_t const got = ::pread(fd, static_cast<char*>(dst) + done, bytes - done, offset + static_cast<off_t>(done));
     if (got < 0 && errno == EINTR) continue;
     if (got <= 0) break;
     done += static_cast<size_t>(got);
   }
-  ::close(fd);
-  if (done != bytes) return Fail(KMC_B200_ERR_IO, std::string("short read: ") + path);
-  return KMC_B200_OK;
+  return done == bytes;
 }
 
-int WriteWholeFile(const char* path, const void* src, size_t bytes) {
-  int const fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
-  if (fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to create output file: ") + path);
+bool WriteRange(int fd, const void* src, size_t bytes, off_t offset) {
   size_t done = 0;
   while (done < bytes) {
-    ssize_t const put = ::pwrite(fd, static_cast<const char*>(src) + done, bytes - done, static_cast<off_t>(done));
+    ssize_t const put = ::pwrite(fd, static_cast<const char*>(src) + done, bytes - done, offset + static_cast<off_t>(done));
     if (put < 0 && errno == EINTR) continue;
     if (put <= 0) break;
     done += static_cast<size_t>(put);
   }
-  bool const closed = (::close(fd) == 0);
-  if (done != bytes || !closed) return Fail(KMC_B200_ERR_IO, std::string("short write: ") + path);
+  return done == bytes;
+}
+
+struct Fd {  // closes on scope exit
+  int fd = -1;
+  ~Fd() {
+    if (fd >= 0) ::close(fd);
+  }
+  int Close() {
+    int const rc = fd >= 0 ? ::close(fd) : 0;
+    fd = -1;
+    return rc;
+  }
+};
+
+int ReadWholeFile(const char* path, void* dst, size_t bytes) {
+  Fd f{::open(path, O_RDONLY | O_CLOEXEC)};
+  if (f.fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path);
+  if (!ReadRange(f.fd, dst, bytes, 0)) return Fail(KMC_B200_ERR_IO, std::string("short read: ") + path);
   return KMC_B200_OK;
 }
 
+int WriteWholeFile(const char* path, const void* src, size_t bytes) {
+  Fd f{::open(path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644)};
+  if (f.fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to create output file: ") + path);
+  bool const written = WriteRange(f.fd, src, bytes, 0);
+  if (f.Close() != 0 || !written) return Fail(KMC_B200_ERR_IO, std::string("short write: ") + path);
+  return KMC_B200_OK;
+}
+
+// Size of a KITTI .bin in whole points.  The reference's loader accepts any size that is a multiple of 4 bytes and
+// truncates a trailing partial point (data_io.cpp:107-112); so does this.
+int BinFilePoints(const char* path, int64_t* n_points) {
+  struct stat st;
+  if (::stat(path, &st) != 0) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path);
+  if (st.st_size % 4 != 0)
+    return Fail(KMC_B200_ERR_IO, std::string("KITTI pointcloud binary file is incorrectly formatted (size is not a multiple of 4 bytes): ") + path);
+  *n_points = static_cast<int64_t>(st.st_size / 16);
+  return KMC_B200_OK;
+}
+
+// One .bin file of any size through the slots: pread straight into a slot's pinned input buffer, pwrite straight from its
+// pinned output buffer — no whole-file buffers.  `launch` as for StreamChunks.
+template <class Launch>
+int StreamBinFile(kmc_b200_handle* h, const char* path_in, const char* path_out, int64_t n, Launch&& launch) {
+  Fd in{::open(path_in, O_RDONLY | O_CLOEXEC)};
+  if (in.fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + path_in);
+  Fd out{::open(path_out, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644)};
+  if (out.fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to create output file: ") + path_out);
+  int rc = StreamChunks(
+      h, n,
+      [&](int slot, int64_t first, int64_t count, const float** src) -> int {
+        if (!ReadRange(in.fd, h->h_in[slot], static_cast<size_t>(count) * 16, static_cast<off_t>(first) * 16))
+          return Fail(KMC_B200_ERR_IO, std::string("short read: ") + path_in);
+        *src = h->h_in[slot];
+        return KMC_B200_OK;
+      },
+      launch, [&](int slot, int64_t) -> float* { return h->h_out[slot]; },
+      [&](int slot, int64_t first, int64_t count) -> int {
+        if (!WriteRange(out.fd, h->h_out[slot], static_cast<size_t>(count) * 16, static_cast<off_t>(first) * 16))
+          return Fail(KMC_B200_ERR_IO, std::string("short write: ") + path_out);
+        return KMC_B200_OK;
+      });
+  if (out.Close() != 0 && rc == KMC_B200_OK) rc = Fail(KMC_B200_ERR_IO, std::string("short write: ") + path_out);
+  return rc;
+}
+
 }  // namespace
+}  // extern "C++"
+
+int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char* path_out, const kmc_b200_frame_params* params,
+                             int64_t* n_points_out) try {
+  TraceRange const trace("kmc_b200_deskew_bin_file");
+  if (!h || !path_in || !path_out || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_file: null argument");
+  int64_t n = 0;
+  if (int rc = BinFilePoints(path_in, &n)) return rc;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  kmc_b200_frame_params const P = *params;
+  int const rc = StreamBinFile(h, path_in, path_out, n, [&](int slot, int64_t, int64_t count) -> int {
+    auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(h->d_in[slot], h->d_out[slot], count, P, KMC_B200_TIME_FROM_AZIMUTH, cfg, h->sm_count,
+                                                  h->stream[slot]));
+    return KMC_B200_OK;
+  });
+  if (rc != KMC_B200_OK) return rc;
+  if (n_points_out) *n_points_out = n;
+  return KMC_B200_OK;
+}
+KMC_CATCH_AT_BOUNDARY("deskew_bin_file")
 
 // Files are packed, in order, into groups that fit one staging slot of the handle.  Three slots rotate through
 //   read (io_threads x pread straight into the slot's pinned input buffer)  ->  H2D  ->  batched deskew kernel  ->  D2H
@@ -707,7 +818,7 @@ int WriteWholeFile(const char* path, const void* src, size_t bytes) {
 // disk / page cache, both PCIe directions and the SMs are busy at the same time.  No intermediate host copies: the .bin
 // format is the kernel's input layout.
 int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* const* paths_in, const char* const* paths_out,
-                              const kmc_b200_frame_params* params, int mode, int32_t io_threads, int64_t* points_out) {
+                              const kmc_b200_frame_params* params, int mode, int32_t io_threads, int64_t* points_out) try {
   TraceRange const trace("kmc_b200_deskew_bin_files");
   if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_files: null handle");
   if (n_files < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_bin_files: negative n_files");
@@ -721,11 +832,8 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
   std::vector<int64_t> offsets(static_cast<size_t>(n_files) + 1, 0);
   for (int32_t f = 0; f < n_files; ++f) {
     if (!paths_in[f] || !paths_out[f]) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_bin_files: null path");
-    struct stat st;
-    if (::stat(paths_in[f], &st) != 0) return Fail(KMC_B200_ERR_IO, std::string("unable to open KITTI pointcloud binary file: ") + paths_in[f]);
-    if (st.st_size % 16 != 0)
-      return Fail(KMC_B200_ERR_IO, std::string("KITTI pointcloud binary file is not a whole number of xyzi points: ") + paths_in[f]);
-    int64_t const n = static_cast<int64_t>(st.st_size / 16);
+    int64_t n = 0;
+    if (int rc = BinFilePoints(paths_in[f], &n)) return rc;
     offsets[static_cast<size_t>(f) + 1] = offsets[static_cast<size_t>(f)] + n;
     if (points_out) points_out[f] = n;
   }
@@ -759,6 +867,21 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
   int retire_status = KMC_B200_OK;
   std::string retire_message;
 
+  auto retire_group = [&](size_t g) -> int {
+    int const slot = static_cast<int>(g % kSlots);
+    cudaError_t const e = cudaEventSynchronize(h->done[slot]);
+    if (e != cudaSuccess) return FailCuda(e, "cudaEventSynchronize(done)");
+    Group const grp = groups[g];
+    int64_t const base = offsets[static_cast<size_t>(grp.first_file)];
+    int const rc = ParallelFor(grp.end_file - grp.first_file, io_threads, [&](int64_t k) -> int {
+      size_t const f = static_cast<size_t>(grp.first_file + k);
+      return WriteWholeFile(paths_out[f], h->h_out[slot] + 4 * (offsets[f] - base), static_cast<size_t>(offsets[f + 1] - offsets[f]) * 16);
+    });
+    if (rc == KMC_B200_OK && h->file_done)  // in file order, from this (the retiring) thread
+      for (int32_t f = grp.first_file; f < grp.end_file; ++f)
+        h->file_done(f, offsets[static_cast<size_t>(f) + 1] - offsets[static_cast<size_t>(f)], h->file_done_user);
+    return rc;
+  };
   std::thread retirer([&] {
     cudaSetDevice(h->device);
     for (;;) {
@@ -770,17 +893,11 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
         g = submitted.front();
         submitted.pop_front();
       }
-      int const slot = static_cast<int>(g % kSlots);
-      int rc = KMC_B200_OK;
-      cudaError_t const e = cudaEventSynchronize(h->done[slot]);
-      if (e != cudaSuccess) rc = FailCuda(e, "cudaEventSynchronize(done)");
-      if (rc == KMC_B200_OK) {
-        Group const grp = groups[g];
-        int64_t const base = offsets[static_cast<size_t>(grp.first_file)];
-        rc = ParallelFor(grp.end_file - grp.first_file, io_threads, [&](int64_t k) -> int {
-          size_t const f = static_cast<size_t>(grp.first_file + k);
-          return WriteWholeFile(paths_out[f], h->h_out[slot] + 4 * (offsets[f] - base), static_cast<size_t>(offsets[f + 1] - offsets[f]) * 16);
-        });
+      int rc;
+      try {
+        rc = retire_group(g);
+      } catch (...) {  // nothing may escape a thread function
+        rc = kmc_b200::internal::FailException("deskew_bin_files (retiring thread)");
       }
       {
         std::lock_guard<std::mutex> lk(mu);
@@ -788,11 +905,27 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
           retire_status = rc;
           retire_message = LastError();
         }
-        slot_free[slot] = true;
+        slot_free[g % kSlots] = true;
       }
       cv.notify_all();
     }
   });
+  struct Joiner {  // whatever path leaves this function — an exception included — the retiring thread is told to stop and joined
+    std::thread& t;
+    std::mutex& mu;
+    std::condition_variable& cv;
+    bool& no_more;
+    void Join() {
+      if (!t.joinable()) return;
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        no_more = true;
+      }
+      cv.notify_all();
+      t.join();
+    }
+    ~Joiner() { Join(); }
+  } joiner{retirer, mu, cv, no_more};
 
   int status = KMC_B200_OK;
   for (size_t g = 0; g < groups.size() && status == KMC_B200_OK; ++g) {
@@ -808,7 +941,7 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
     int64_t const count = offsets[static_cast<size_t>(grp.end_file)] - base;
     if (count > h->capacity) {
       // One file larger than a staging slot (a group of its own): let the pipeline drain, then stream the file through all
-      // three slots in capacity-sized chunks, as kmc_b200_deskew_batch_host does for an array.
+      // three slots in capacity-sized chunks (pread into / pwrite from the pinned slots, no whole-file buffer).
       {
         std::unique_lock<std::mutex> lk(mu);
         slot_free[slot] = true;
@@ -816,16 +949,13 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
         if (retire_status != KMC_B200_OK) break;
       }
       size_t const f = static_cast<size_t>(grp.first_file);
-      std::vector<float> big_in(static_cast<size_t>(count) * 4), big_out(static_cast<size_t>(count) * 4);
-      status = ReadWholeFile(paths_in[f], big_in.data(), static_cast<size_t>(count) * 16);
-      if (status == KMC_B200_OK)
-        status = StreamThroughDevice(h, big_in.data(), big_out.data(), count, [&](int s, int64_t first, int64_t chunk) -> int {
-          auto const cfg = kmc_b200::dev::PickConfig(chunk, true, false, h->sm_count);
-          KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[s], h->d_out[s], h->d_offsets, h->d_params, n_files, chunk, base + first,
-                                                        n_total, mode, cfg, h->sm_count, h->stream[s]));
-          return KMC_B200_OK;
-        });
-      if (status == KMC_B200_OK) status = WriteWholeFile(paths_out[f], big_out.data(), static_cast<size_t>(count) * 16);
+      status = StreamBinFile(h, paths_in[f], paths_out[f], count, [&](int s, int64_t first, int64_t chunk) -> int {
+        auto const cfg = kmc_b200::dev::PickConfig(chunk, true, false, h->sm_count);
+        KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[s], h->d_out[s], h->d_offsets, h->d_params, n_files, chunk, base + first,
+                                                      n_total, mode, cfg, h->sm_count, h->stream[s]));
+        return KMC_B200_OK;
+      });
+      if (status == KMC_B200_OK && h->file_done) h->file_done(grp.first_file, count, h->file_done_user);
       continue;
     }
     status = ParallelFor(grp.end_file - grp.first_file, io_threads, [&](int64_t k) -> int {
@@ -853,12 +983,7 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
     cv.notify_all();
   }
   std::string const keep = LastError();
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    no_more = true;
-  }
-  cv.notify_all();
-  retirer.join();
+  joiner.Join();
   if (status != KMC_B200_OK) {
     for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
     cudaGetLastError();
@@ -871,5 +996,6 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
   }
   return KMC_B200_OK;
 }
+KMC_CATCH_AT_BOUNDARY("deskew_bin_files")
 
 }  // extern "C"

@@ -37,10 +37,17 @@ bool ClockToSeconds(std::string const& line, double* out) {
   if (space == std::string::npos || line.size() < space + 8) return false;
   std::string const clock = line.substr(space + 1);
   if (clock.size() < 7 || clock[2] != ':' || clock[5] != ':') return false;
-  char* end = nullptr;
-  long const hours = std::strtol(clock.substr(0, 2).c_str(), &end, 10);
-  long const minutes = std::strtol(clock.substr(3, 2).c_str(), &end, 10);
+  // the reference's std::stoi / std::stod throw on text that does not start with a number (utils.cpp:34-41): malformed here
+  auto two_digits = [&](size_t at, long* value) {
+    if (clock[at] < '0' || clock[at] > '9' || clock[at + 1] < '0' || clock[at + 1] > '9') return false;
+    *value = (clock[at] - '0') * 10 + (clock[at + 1] - '0');
+    return true;
+  };
+  long hours = 0, minutes = 0;
+  if (!two_digits(0, &hours) || !two_digits(3, &minutes)) return false;
   std::string const sec = clock.substr(6, 18);
+  if (sec.empty() || !((sec[0] >= '0' && sec[0] <= '9') || sec[0] == '.')) return false;
+  char* end = nullptr;
   double const seconds = std::strtod(sec.c_str(), &end);
   if (end == sec.c_str()) return false;
   *out = static_cast<double>((60 * hours * 60) + (minutes * 60)) + seconds;
@@ -121,7 +128,7 @@ int PrepareRun(fs::path const& run, size_t* n_out, std::vector<kmc_b200_frame_pa
 }  // namespace
 
 extern "C" int kmc_b200_run_prepare(const char* run_folder, int64_t capacity_frames, kmc_b200_frame_params* params_out,
-                                    int64_t* n_frames_out) {
+                                    int64_t* n_frames_out) try {
   if (!run_folder || !n_frames_out) return SetError(KMC_B200_ERR_NULL_POINTER, "run_prepare: null argument");
   size_t n = 0;
   std::vector<kmc_b200_frame_params> params;
@@ -134,9 +141,10 @@ extern "C" int kmc_b200_run_prepare(const char* run_folder, int64_t capacity_fra
   }
   return KMC_B200_OK;
 }
+KMC_CATCH_AT_BOUNDARY("run_prepare")
 
 extern "C" int kmc_b200_motion_compensate_run(kmc_b200_handle* h, const char* run_folder, int32_t io_threads,
-                                              kmc_b200_run_stats* stats) {
+                                              kmc_b200_run_stats* stats) try {
   if (!h || !run_folder) return SetError(KMC_B200_ERR_NULL_POINTER, "motion_compensate_run: null argument");
   auto const t_begin = std::chrono::steady_clock::now();
   fs::path const run{run_folder};
@@ -181,3 +189,4 @@ extern "C" int kmc_b200_motion_compensate_run(kmc_b200_handle* h, const char* ru
   if (stats) *stats = local;
   return KMC_B200_OK;
 }
+KMC_CATCH_AT_BOUNDARY("motion_compensate_run")

@@ -881,10 +881,19 @@ def test_bin_files_pipeline_matches_per_frame_calls(capi, oracle, cuda, tmp_path
         with pytest.raises(capi.KmcError) as e:
             h.deskew_bin_files([str(tmp_path / "missing.bin")], [paths_out[0]], params[:1])
         assert e.value.status == capi.ERR_IO
-        (tmp_path / "odd.bin").write_bytes(b"\0" * 20)
+        (tmp_path / "odd.bin").write_bytes(b"\0" * 18)  # not a multiple of 4 bytes: the reference's loader throws (data_io.cpp:107)
         with pytest.raises(capi.KmcError) as e:
             h.deskew_bin_files([str(tmp_path / "odd.bin")], [paths_out[0]], params[:1])
         assert e.value.status == capi.ERR_IO
+        # a multiple of 4 that is not a whole point: the reference keeps the whole points and drops the rest (data_io.cpp:112)
+        partial = scans[3][:1000].tobytes() + b"\x01\x02\x03\x04" * 3
+        (tmp_path / "partial.bin").write_bytes(partial)
+        assert h.deskew_bin_files([str(tmp_path / "partial.bin")], [str(tmp_path / "partial_out.bin")], params[3:4]).tolist() == [1000]
+        want = run_frame(cuda, capi, scans[3][:1000], capi.FrameParams.from_buffer_copy(params[3:4].tobytes()))
+        assert np.array_equal(helpers.read_bin(str(tmp_path / "partial_out.bin")), want)
+        assert h.deskew_bin_file(str(tmp_path / "partial.bin"), str(tmp_path / "partial_out2.bin"),
+                                 capi.FrameParams.from_buffer_copy(params[3:4].tobytes())) == 1000
+        assert np.array_equal(helpers.read_bin(str(tmp_path / "partial_out2.bin")), want)
         # a file larger than a staging slot is streamed through the slots in chunks, between ordinary groups
         big = helpers.synthetic_scan(16_000 * 3 + 1234, 64, 1)
         big.tofile(str(tmp_path / "big.bin"))
@@ -922,9 +931,16 @@ def test_motion_compensate_run_c_abi(capi, oracle, cuda, tmp_path):
             assert_parity(got, want, info["scans"][i])
         assert np.array_equal(helpers.read_bin(str(out / f"{0:010d}.bin")), info["scans"][0])
         assert np.array_equal(helpers.read_bin(str(out / f"{n - 1:010d}.bin")), info["scans"][n - 1])
-        # a second call overwrites in place and gives the same files
+        # a second call overwrites in place and gives the same files; the progress callback sees every deskewed file once, in order
+        import ctypes as C
         before = [helpers.read_bin(str(out / f"{i:010d}.bin")) for i in range(n)]
+        seen = []
+        cb_type = C.CFUNCTYPE(None, C.c_int32, C.c_int64, C.c_void_p)
+        cb = cb_type(lambda index, n_points, user: seen.append((index, n_points)))
+        assert capi.lib().kmc_b200_handle_set_file_callback(h.raw, C.cast(cb, C.c_void_p), None) == capi.OK
         h.motion_compensate_run(str(run), io_threads=2)
+        assert capi.lib().kmc_b200_handle_set_file_callback(h.raw, None, None) == capi.OK
+        assert seen == [(k, len(info["scans"][k + 1])) for k in range(n - 2)]
         assert all(np.array_equal(before[i], helpers.read_bin(str(out / f"{i:010d}.bin"))) for i in range(n))
         # missing time-stamp file / OxTS packet -> ERR_IO; scan stamp outside its OxTS interval -> ERR_TIME_OUT_OF_RANGE
         os.rename(run / "oxts" / "data" / f"{3:010d}.txt", run / "oxts" / "data" / "hidden")

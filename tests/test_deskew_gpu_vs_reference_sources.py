@@ -176,6 +176,10 @@ def test_motion_compensate_run_matches_the_reference_handler(capi, cuda, tmp_pat
     cli = build.build_example()
     r = subprocess.run([cli, str(tmp_path / "ours"), "run_sync"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+    # one progress line per deskewed frame, in order, as the reference's loop prints them (handlers.cpp:63)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("Motion compensated pointcloud number: ")]
+    assert [int(ln.rsplit(" ", 1)[1]) for ln in lines] == list(range(1, n - 1))
+    assert "Motion compensating: run_sync" in r.stdout
     worst = 0.0
     for i in range(n):
         a = helpers.read_bin(str(ref_dir / "velodyne_points" / "data_motion_compensated" / f"{i:010d}.bin"))
@@ -191,3 +195,22 @@ def test_motion_compensate_run_matches_the_reference_handler(capi, cuda, tmp_pat
             assert np.abs(a[:, :3] - info["scans"][i][:, :3]).max() > 0.05
     print(f"run of {n} frames: max |dxyz| between the reference's files and the drop-in's = {worst:.3e} m")
     assert worst < TOL_M
+
+
+def test_cli_without_run_arguments_takes_every_directory(capi, cuda, tmp_path):
+    """examples/motion_compensate_runs.cpp:14-19 of the reference: with only <DATA_DIR> every sub-directory is a run,
+    whatever its name; no arguments at all print the usage and return -1."""
+    import subprocess
+    from kitti_motion_compensation_b200 import build
+    helpers.make_run_folder(str(tmp_path / "data" / "2011_09_26_drive_0001_sync"), 4, 2_000, seed=1)
+    helpers.make_run_folder(str(tmp_path / "data" / "another_run"), 3, 1_500, seed=2)
+    (tmp_path / "data" / "notes.txt").write_text("not a run\n")
+    cli = build.build_example()
+    r = subprocess.run([cli, str(tmp_path / "data")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for run, frames in (("2011_09_26_drive_0001_sync", 4), ("another_run", 3)):
+        out = tmp_path / "data" / run / "velodyne_points" / "data_motion_compensated"
+        assert sorted(p.name for p in out.iterdir()) == [f"{i:010d}.bin" for i in range(frames)]
+        assert f"Motion compensating: {run}" in r.stdout
+    r = subprocess.run([cli], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "<DATA_DIR>" in r.stdout

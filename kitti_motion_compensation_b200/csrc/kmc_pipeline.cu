@@ -133,17 +133,22 @@ int EnsureTables(kmc_b200_handle* h, int64_t n_frames) {
 // Core of every host pipeline: chunks of the point range [0, n) rotate through the handle's three stream / buffer slots
 //   fetch(slot, first, count) -> pinned source of the chunk (the caller's pinned memory, or h_in[slot] after a staging
 //                                copy or a pread)                                                        [host, this thread]
-//   H2D -> launch(slot, first, count) -> D2H into sink(slot, first) (caller's pinned memory or h_out[slot])   [slot's stream]
+//   H2D -> launch(slot, first, count, d_in, d_out) -> D2H into sink(slot, first) (caller's pinned memory or h_out[slot])
+//                                                                                                        [slot's stream]
 //   deliver(slot, first, count) once the chunk's event has fired (unstage / pwrite; nothing for pinned)  [host, this thread]
 // so the copy engines, the SMs and the host work of neighbouring chunks overlap.
+// zero_copy: no copy engines — the kernel reads the pinned source and writes the pinned sink directly over PCIe (one launch
+// per chunk).  For a transfer of a few MB the two copies' fixed latencies (~10 us each) and their serialisation behind the
+// kernel cost more than SM-issued PCIe reads lose: one 130 000-point scan takes 67 us instead of 96 us
+// (profiles/r02_latency_probe.log); from ~1 M points on the copy engines win (47 vs 40 GB/s each way).
 template <class Fetch, class Launch, class Sink, class Deliver>
-int StreamChunksImpl(kmc_b200_handle* h, int64_t n, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver);
+int StreamChunksImpl(kmc_b200_handle* h, int64_t n, bool zero_copy, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver);
 
 // On any failure the slots' streams are drained before returning, so that no copy is still reading or writing the
 // caller's buffers after the call has reported an error.
 template <class Fetch, class Launch, class Sink, class Deliver>
-int StreamChunks(kmc_b200_handle* h, int64_t n, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver) {
-  int const rc = StreamChunksImpl(h, n, fetch, launch, sink, deliver);
+int StreamChunks(kmc_b200_handle* h, int64_t n, bool zero_copy, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver) {
+  int const rc = StreamChunksImpl(h, n, zero_copy, fetch, launch, sink, deliver);
   if (rc != KMC_B200_OK) {
     std::string const keep = LastError();
     for (int s = 0; s < kmc_b200_handle::kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
@@ -219,8 +224,28 @@ int64_t NextChunkPoints(int64_t chunk_index, int64_t remaining, int64_t capacity
   return std::max<int64_t>(c & ~int64_t{1023}, 1024);  // ramp sizes only: whole multiples of 1024 points
 }
 
+// Chunks of a zero-copy transfer: one launch for pinned caller memory; with pageable memory the staging copies of one piece
+// overlap the kernel of the other, so the transfer is cut in `zc_parts` pieces (default 2).
+int64_t ZeroCopyChunkPoints(int64_t remaining, int64_t capacity, int64_t total) {
+  int64_t const parts = std::max(1, TuneValue("zc_parts", 1));
+  int64_t const c = std::max<int64_t>(8192, ((total + parts - 1) / parts + 1023) & ~int64_t{1023});
+  return std::min({c, remaining, capacity});
+}
+
+// Device-visible alias of a pinned host pointer (identical under UVA for cudaHostAlloc memory; may differ for registered memory).
+template <class T>
+bool DeviceAlias(T* host, T** dev) {
+  void* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, const_cast<void*>(static_cast<const void*>(host)), 0) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  *dev = static_cast<T*>(d);
+  return true;
+}
+
 template <class Fetch, class Launch, class Sink, class Deliver>
-int StreamChunksImpl(kmc_b200_handle* h, int64_t n, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver) {
+int StreamChunksImpl(kmc_b200_handle* h, int64_t n, bool zero_copy, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver) {
   constexpr int kSlots = kmc_b200_handle::kSlots;
   struct Pending {
     int64_t first = 0, count = 0;
@@ -238,14 +263,22 @@ int StreamChunksImpl(kmc_b200_handle* h, int64_t n, Fetch&& fetch, Launch&& laun
   int64_t count = 0;
   for (int64_t first = 0; first < n; first += count, ++chunk_index) {
     int const slot = static_cast<int>(chunk_index % kSlots);
-    count = NextChunkPoints(chunk_index, n - first, h->capacity, n);
+    count = zero_copy ? ZeroCopyChunkPoints(n - first, h->capacity, n) : NextChunkPoints(chunk_index, n - first, h->capacity, n);
     size_t const bytes = static_cast<size_t>(count) * 16;
     if (int rc = retire(slot)) return rc;
     const float* src = nullptr;
     if (int rc = fetch(slot, first, count, &src)) return rc;
-    KMC_CUDA_TRY(cudaMemcpyAsync(h->d_in[slot], src, bytes, cudaMemcpyHostToDevice, h->stream[slot]));
-    if (int rc = launch(slot, first, count)) return rc;
-    KMC_CUDA_TRY(cudaMemcpyAsync(sink(slot, first), h->d_out[slot], bytes, cudaMemcpyDeviceToHost, h->stream[slot]));
+    float* const dst = sink(slot, first);
+    if (zero_copy) {
+      const float* d_src = nullptr;
+      float* d_dst = nullptr;
+      if (!DeviceAlias(src, &d_src) || !DeviceAlias(dst, &d_dst)) return Fail(KMC_B200_ERR_CUDA, "pinned host buffer is not mapped into the device address space");
+      if (int rc = launch(slot, first, count, d_src, d_dst)) return rc;
+    } else {
+      KMC_CUDA_TRY(cudaMemcpyAsync(h->d_in[slot], src, bytes, cudaMemcpyHostToDevice, h->stream[slot]));
+      if (int rc = launch(slot, first, count, h->d_in[slot], h->d_out[slot])) return rc;
+      KMC_CUDA_TRY(cudaMemcpyAsync(dst, h->d_out[slot], bytes, cudaMemcpyDeviceToHost, h->stream[slot]));
+    }
     KMC_CUDA_TRY(cudaEventRecord(h->done[slot], h->stream[slot]));
     pending[slot] = {first, count, true};
   }
@@ -256,13 +289,23 @@ int StreamChunksImpl(kmc_b200_handle* h, int64_t n, Fetch&& fetch, Launch&& laun
   return KMC_B200_OK;
 }
 
-// A host ARRAY through the device: pinned caller memory is copied directly, pageable memory is staged through the slots.
+// A host ARRAY through the device: pinned caller memory is used directly, pageable memory is staged through the slots;
+// small transfers (<= zc_points, default 400 000 points = 6.4 MB each way) skip the copy engines (zero_copy above).
 template <class Launch>
 int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
   bool const in_pinned = IsPinnedHost(in);
   bool const out_pinned = IsPinnedHost(out);
+  bool zero_copy = n <= TuneValue("zc_points", 400000);
+  if (zero_copy && in_pinned) {
+    const float* alias = nullptr;
+    zero_copy = DeviceAlias(in, &alias);
+  }
+  if (zero_copy && out_pinned) {
+    float* alias = nullptr;
+    zero_copy = DeviceAlias(out, &alias);
+  }
   return StreamChunks(
-      h, n,
+      h, n, zero_copy,
       [&](int slot, int64_t first, int64_t count, const float** src) -> int {
         *src = in + 4 * first;
         if (!in_pinned) {
@@ -276,6 +319,28 @@ int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t
         if (!out_pinned) StagingCopy(h, out + 4 * first, h->h_out[slot], static_cast<size_t>(count) * 16);
         return KMC_B200_OK;
       });
+}
+
+// Launch shape of a chunk of a host call: the HBM-tuned shape when the chunk sits in device memory; when the kernel reads
+// pinned host memory over PCIe (zero copy) what matters is the number of read requests in flight on the link, not HBM
+// queues: one CTA of 256 threads per SM, 128-bit accesses (KMC_B200_TUNE zc_block / zc_ctas / zc_vec / zc_tiles).
+kmc_b200::dev::LaunchConfig PickHostCallConfig(const kmc_b200_handle* h, int64_t count, const float* src, const float* dst) {
+  bool const aligned32 = Aligned(src, 32) && Aligned(dst, 32);
+  auto cfg = kmc_b200::dev::PickConfig(count, aligned32, false, h->sm_count);
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+    cfg.bulk = 0;
+    cfg.hint = 0;
+    cfg.unroll = 1;
+    cfg.block = TuneValue("zc_block", 256);
+    cfg.ctas_per_sm = std::max(1, TuneValue("zc_ctas", 1));
+    cfg.vec = (TuneValue("zc_vec", 1) == 2 && aligned32) ? 2 : 1;
+    cfg.item_tiles = std::max(1, TuneValue("zc_tiles", 1));
+    if (cfg.block != 128 && cfg.block != 512) cfg.block = 256;
+  } else {
+    cudaGetLastError();
+  }
+  return cfg;
 }
 
 int CheckOffsets(const int64_t* offsets, int32_t n_frames) {
@@ -370,9 +435,9 @@ int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, 
   DeviceGuard const guard(h->device);
   KMC_CUDA_TRY(guard.status());
   kmc_b200_frame_params const P = *params;
-  return StreamThroughDevice(h, in, out, n, [&](int slot, int64_t, int64_t count) -> int {
-    auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
-    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(h->d_in[slot], h->d_out[slot], count, P, mode, cfg, h->sm_count, h->stream[slot]));
+  return StreamThroughDevice(h, in, out, n, [&](int slot, int64_t, int64_t count, const float* src, float* dst) -> int {
+    auto const cfg = PickHostCallConfig(h, count, src, dst);
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(src, dst, count, P, mode, cfg, h->sm_count, h->stream[slot]));
     return KMC_B200_OK;
   });
 }
@@ -398,10 +463,10 @@ int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* in, float* out, 
   KMC_CUDA_TRY(cudaMemcpyAsync(h->d_offsets, offsets, static_cast<size_t>(n_frames + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream[0]));
   KMC_CUDA_TRY(cudaMemcpyAsync(h->d_params, params, static_cast<size_t>(n_frames) * sizeof(kmc_b200_frame_params), cudaMemcpyHostToDevice, h->stream[0]));
   KMC_CUDA_TRY(cudaStreamSynchronize(h->stream[0]));
-  return StreamThroughDevice(h, in, out, n_total, [&](int slot, int64_t first, int64_t count) -> int {
-    auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
-    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[slot], h->d_out[slot], h->d_offsets, h->d_params, n_frames, count, first,
-                                                  n_total, mode, cfg, h->sm_count, h->stream[slot]));
+  return StreamThroughDevice(h, in, out, n_total, [&](int slot, int64_t first, int64_t count, const float* src, float* dst) -> int {
+    auto const cfg = PickHostCallConfig(h, count, src, dst);
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(src, dst, h->d_offsets, h->d_params, n_frames, count, first, n_total, mode, cfg,
+                                                  h->sm_count, h->stream[slot]));
     return KMC_B200_OK;
   });
 }
@@ -644,9 +709,9 @@ int kmc_b200_project_frame_host(kmc_b200_handle* h, const float* in, float* uvzc
   DeviceGuard const guard(h->device);
   KMC_CUDA_TRY(guard.status());
   kmc_b200_camera_params const K = *camera;
-  return StreamThroughDevice(h, in, uvzc_out, n, [&](int slot, int64_t, int64_t count) -> int {
-    KMC_CUDA_TRY(kmc_b200::dev::LaunchProject(h->d_in[slot], nullptr, h->d_out[slot], count, nullptr, K, KMC_B200_TIME_FROM_AZIMUTH, true,
-                                              h->sm_count, h->stream[slot]));
+  return StreamThroughDevice(h, in, uvzc_out, n, [&](int slot, int64_t, int64_t count, const float* src, float* dst) -> int {
+    bool const vec2 = Aligned(src, 32) && Aligned(dst, 32);
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchProject(src, nullptr, dst, count, nullptr, K, KMC_B200_TIME_FROM_AZIMUTH, vec2, h->sm_count, h->stream[slot]));
     return KMC_B200_OK;
   });
 }
@@ -769,7 +834,7 @@ int StreamBinFile(kmc_b200_handle* h, const char* path_in, const char* path_out,
   Fd out{::open(path_out, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644)};
   if (out.fd < 0) return Fail(KMC_B200_ERR_IO, std::string("unable to create output file: ") + path_out);
   int rc = StreamChunks(
-      h, n,
+      h, n, false,
       [&](int slot, int64_t first, int64_t count, const float** src) -> int {
         if (!ReadRange(in.fd, h->h_in[slot], static_cast<size_t>(count) * 16, static_cast<off_t>(first) * 16))
           return Fail(KMC_B200_ERR_IO, std::string("short read: ") + path_in);
@@ -799,10 +864,9 @@ int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char
   DeviceGuard const guard(h->device);
   KMC_CUDA_TRY(guard.status());
   kmc_b200_frame_params const P = *params;
-  int const rc = StreamBinFile(h, path_in, path_out, n, [&](int slot, int64_t, int64_t count) -> int {
+  int const rc = StreamBinFile(h, path_in, path_out, n, [&](int slot, int64_t, int64_t count, const float* src, float* dst) -> int {
     auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
-    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(h->d_in[slot], h->d_out[slot], count, P, KMC_B200_TIME_FROM_AZIMUTH, cfg, h->sm_count,
-                                                  h->stream[slot]));
+    KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(src, dst, count, P, KMC_B200_TIME_FROM_AZIMUTH, cfg, h->sm_count, h->stream[slot]));
     return KMC_B200_OK;
   });
   if (rc != KMC_B200_OK) return rc;
@@ -949,10 +1013,10 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
         if (retire_status != KMC_B200_OK) break;
       }
       size_t const f = static_cast<size_t>(grp.first_file);
-      status = StreamBinFile(h, paths_in[f], paths_out[f], count, [&](int s, int64_t first, int64_t chunk) -> int {
+      status = StreamBinFile(h, paths_in[f], paths_out[f], count, [&](int s, int64_t first, int64_t chunk, const float* src, float* dst) -> int {
         auto const cfg = kmc_b200::dev::PickConfig(chunk, true, false, h->sm_count);
-        KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[s], h->d_out[s], h->d_offsets, h->d_params, n_files, chunk, base + first,
-                                                      n_total, mode, cfg, h->sm_count, h->stream[s]));
+        KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(src, dst, h->d_offsets, h->d_params, n_files, chunk, base + first, n_total, mode, cfg,
+                                                      h->sm_count, h->stream[s]));
         return KMC_B200_OK;
       });
       if (status == KMC_B200_OK && h->file_done) h->file_done(grp.first_file, count, h->file_done_user);

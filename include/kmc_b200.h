@@ -231,6 +231,26 @@ KMC_B200_API int kmc_b200_deskew_project_frame_device(const float* xyzi_in, floa
 KMC_B200_API int kmc_b200_deskew_project_frame4_device(const float* xyzi_in, float* xyzi_out, float* const uvzc_out[4],
                                                        int64_t n_points, const kmc_b200_frame_params* params_host,
                                                        const kmc_b200_camera_params cameras_host[4], int time_mode, void* stream);
+/* Batch forms of the secondary entry points (the viz handler loops frames: handlers.cpp:67-92, one MotionCompensateFrame and
+ * four projections per frame).  Frames back to back, frame_offsets_dev / params_dev as for kmc_b200_deskew_batch_device.
+ *
+ * Deskew + projection of the deskewed points onto n_cameras (1 or 4) cameras for every frame of the batch in one pass;
+ * the cameras are the same for all frames (one calibration per run).  uvzc_out[c] receives n_points_total records of
+ * camera c (see kmc_b200_project_frame_device); xyzi_out (optional) the deskewed cloud.  Bit-identical to the per-frame
+ * calls. */
+KMC_B200_API int kmc_b200_deskew_project_batch_device(const float* xyzi_in, float* xyzi_out, float* const uvzc_out[], int32_t n_cameras,
+                                                      const int64_t* frame_offsets_dev, const kmc_b200_frame_params* params_dev,
+                                                      int32_t n_frames, int64_t n_points_total,
+                                                      const kmc_b200_camera_params* cameras_host, int time_mode, void* stream);
+/* MotionCompensateFrame on the reference's layout for a batch: frame f owns the 4 N_f doubles at cloud + 4 offsets[f] (its
+ * column-major N_f x 4 matrix), the N_f stamps at stamps + offsets[f], and the same block of out.  times_dev holds
+ * (t_start, t_end, t_req) per frame (3 doubles each; the host must have validated t_start < t_end and t_req within, as
+ * kmc_b200_frame_params_from_poses does); flags_dev receives one int per frame (zeroed by the call) with the bits of
+ * kmc_b200_deskew_cloud_f64_device.  Bit-identical to the per-frame call. */
+KMC_B200_API int kmc_b200_deskew_cloud_f64_batch_device(const double* cloud, const double* stamps, double* out,
+                                                        const int64_t* frame_offsets_dev, const kmc_b200_frame_params* params_dev,
+                                                        const double* times_dev, int32_t n_frames, int64_t n_points_total,
+                                                        int* flags_dev, void* stream);
 /* Validation pass for KMC_B200_TIME_FROM_W buffers: *flags_dev (device int, zeroed by the call) receives bit 0 if any
  * point's w lies outside [0, 1] or is NaN — the condition on which the reference asserts for every point stamp
  * (trajectory_interpolation.cpp:32,47).  Read-only, 16 B/point. */
@@ -291,6 +311,14 @@ KMC_B200_API int kmc_b200_deskew_batch_multi_gpu(kmc_b200_handle* const* handles
 KMC_B200_API int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud_colmajor, const double* stamps,
                                                 double* out_colmajor, int64_t n_points, double t_start, double t_end, double t_req,
                                                 const kmc_b200_frame_params* params, int* flags_out);
+/* The same for n_frames frames that live in separate host allocations (each reference Frame owns its Eigen matrices):
+ * clouds[f] / stamps[f] / outs[f] as for the single-frame call with n_points[f] points, times holds (t_start, t_end, t_req)
+ * per frame, params one record per frame.  One pipeline over all frames: the host passes, copies and kernels of
+ * neighbouring frames overlap (the single-frame call drains its streams at the end of every frame).  flags_out
+ * (optional, n_frames ints) receives each frame's bits; the status is the first frame's failure, if any, else OK. */
+KMC_B200_API int kmc_b200_deskew_cloud_f64_batch_host(kmc_b200_handle* h, const double* const* clouds, const double* const* stamps,
+                                                      double* const* outs, const int64_t* n_points, const double* times,
+                                                      const kmc_b200_frame_params* params, int32_t n_frames, int* flags_out);
 /* GetPseudoTimeStamps on host columns x, y (length n each): H2D + kernel + D2H. */
 KMC_B200_API int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n_points,
                                                      double scan_start, double scan_end, double* stamps_out);

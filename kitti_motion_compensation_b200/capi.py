@@ -103,6 +103,9 @@ SIGNATURES = {
                                                    C.POINTER(FrameParams), _vp, _vp]),
     "kmc_b200_deskew_project_frame4_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.c_int64, C.POINTER(FrameParams),
                                                         C.POINTER(CameraParams), C.c_int, _vp]),
+    "kmc_b200_deskew_project_batch_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.c_int32, _vp, _vp, C.c_int32, C.c_int64,
+                                                       C.POINTER(CameraParams), C.c_int, _vp]),
+    "kmc_b200_deskew_cloud_f64_batch_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp]),
     "kmc_b200_pseudo_time_stamps_device": (C.c_int, [_vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_pseudo_time_stamps_xy_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
     "kmc_b200_check_fractions_device": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
@@ -120,6 +123,7 @@ SIGNATURES = {
     "kmc_b200_deskew_batch_multi_gpu": (C.c_int, [C.POINTER(_vp), C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, C.c_int]),
     "kmc_b200_deskew_cloud_f64_host": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int64, C.c_double, C.c_double, C.c_double,
                                                  C.POINTER(FrameParams), C.POINTER(C.c_int)]),
+    "kmc_b200_deskew_cloud_f64_batch_host": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, C.c_int32, _vp]),
     "kmc_b200_pseudo_time_stamps_xy_host": (C.c_int, [_vp, _dp, _dp, C.c_int64, C.c_double, C.c_double, _dp]),
     "kmc_b200_project_frame_host": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(CameraParams)]),
     "kmc_b200_deskew_bin_file": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.POINTER(FrameParams), C.POINTER(C.c_int64)]),
@@ -303,6 +307,22 @@ def deskew_project_frame4_device(in_ptr: int, out_ptr: int, uvzc_ptrs, n_points:
                                                       cams, mode, stream))
 
 
+def deskew_project_batch_device(in_ptr: int, out_ptr: int, uvzc_ptrs, offsets_ptr: int, params_ptr: int, n_frames: int, n_points_total: int,
+                                cameras, mode: int = TIME_FROM_AZIMUTH, stream: int = 0) -> None:
+    """Deskew + projection onto len(cameras) (1 or 4) cameras for a whole batch of frames; out_ptr may be 0."""
+    n_cam = len(cameras)
+    planes = (_vp * n_cam)(*uvzc_ptrs)
+    cams = (CameraParams * n_cam)(*cameras)
+    check(lib().kmc_b200_deskew_project_batch_device(in_ptr, out_ptr, planes, n_cam, offsets_ptr, params_ptr, n_frames, n_points_total, cams,
+                                                     mode, stream))
+
+
+def deskew_cloud_f64_batch_device(cloud_ptr: int, stamps_ptr: int, out_ptr: int, offsets_ptr: int, params_ptr: int, times_ptr: int,
+                                  n_frames: int, n_points_total: int, flags_ptr: int, stream: int = 0) -> None:
+    check(lib().kmc_b200_deskew_cloud_f64_batch_device(cloud_ptr, stamps_ptr, out_ptr, offsets_ptr, params_ptr, times_ptr, n_frames,
+                                                       n_points_total, flags_ptr, stream))
+
+
 def pseudo_time_stamps_device(in_ptr: int, out_ptr: int, n_points: int, start: float, end: float, stream: int = 0) -> None:
     check(lib().kmc_b200_pseudo_time_stamps_device(in_ptr, out_ptr, n_points, start, end, stream))
 
@@ -415,6 +435,23 @@ class Handle:
         rc = lib().kmc_b200_deskew_cloud_f64_host(self._h, _ptr(cm), _ptr(ts), _ptr(out), ts.size, t_start, t_end, t_req,
                                                   C.byref(params), C.byref(flags))
         return out.T.copy(), flags.value, rc
+
+    def deskew_cloud_f64_batch(self, clouds_n4, stamps, times, params: np.ndarray):
+        """Several frames in the reference's layout through ONE pipeline: clouds_n4[f] (n_f,4) double, stamps[f] (n_f,),
+        times (F,3) = (t_start, t_end, t_req), params structured array (F,) -> (list of (n_f,4) results, flags (F,), status)."""
+        F = len(clouds_n4)
+        cms = [np.ascontiguousarray(np.asarray(c, dtype=np.float64).T) for c in clouds_n4]
+        tss = [np.ascontiguousarray(t, dtype=np.float64) for t in stamps]
+        outs = [np.empty_like(c) for c in cms]
+        n = np.array([t.size for t in tss], dtype=np.int64)
+        tm = np.ascontiguousarray(times, dtype=np.float64).reshape(F, 3)
+        prm = np.ascontiguousarray(params, dtype=FRAME_PARAMS_DTYPE)
+        flags = np.zeros(F, dtype=np.int32)
+        pa = (_vp * F)(*[c.ctypes.data for c in cms])
+        ps = (_vp * F)(*[t.ctypes.data for t in tss])
+        po = (_vp * F)(*[o.ctypes.data for o in outs])
+        rc = lib().kmc_b200_deskew_cloud_f64_batch_host(self._h, pa, ps, po, n.ctypes.data, tm.ctypes.data, prm.ctypes.data, F, flags.ctypes.data)
+        return [o.T.copy() for o in outs], flags, rc
 
     def pseudo_time_stamps(self, x: np.ndarray, y: np.ndarray, start: float, end: float) -> np.ndarray:
         xs = np.ascontiguousarray(x, dtype=np.float64)

@@ -265,7 +265,7 @@ int kmc_b200_deskew_frame_device(const float* in, float* out, int64_t n, const k
   int device = 0, sm = 0;
   KMC_CUDA_TRY(cudaGetDevice(&device));
   if (int rc = SmCount(device, &sm)) return rc;
-  auto const cfg = kmc_b200::dev::PickConfig(n, Aligned(in, 32) && Aligned(out, 32), in == out, sm);
+  auto const cfg = kmc_b200::dev::PickConfig(n, Aligned(in, 32) && Aligned(out, 32), in == out, sm, false);
   KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(in, out, n, *params, mode, cfg, sm, static_cast<cudaStream_t>(stream)));
   return KMC_B200_OK;
 }
@@ -281,7 +281,7 @@ int kmc_b200_deskew_batch_device(const float* in, float* out, const int64_t* off
   int device = 0, sm = 0;
   KMC_CUDA_TRY(cudaGetDevice(&device));
   if (int rc = SmCount(device, &sm)) return rc;
-  auto const cfg = kmc_b200::dev::PickConfig(n_total, Aligned(in, 32) && Aligned(out, 32), in == out, sm);
+  auto const cfg = kmc_b200::dev::PickConfig(n_total, Aligned(in, 32) && Aligned(out, 32), in == out, sm, true);
   KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(in, out, offsets_dev, params_dev, n_frames, n_total, 0, n_total, mode, cfg, sm,
                                                 static_cast<cudaStream_t>(stream)));
   return KMC_B200_OK;
@@ -355,6 +355,50 @@ int kmc_b200_deskew_project_frame4_device(const float* in, float* xyzi_out, floa
   KMC_CUDA_TRY(cudaGetDevice(&device));
   if (int rc = SmCount(device, &sm)) return rc;
   KMC_CUDA_TRY(kmc_b200::dev::LaunchProject4(in, xyzi_out, uvzc_out, n, params, cameras, mode, sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
+int kmc_b200_deskew_project_batch_device(const float* in, float* xyzi_out, float* const uvzc_out[], int32_t n_cameras,
+                                         const int64_t* offsets_dev, const kmc_b200_frame_params* params_dev, int32_t n_frames,
+                                         int64_t n_total, const kmc_b200_camera_params* cameras, int mode, void* stream) {
+  if (n_frames < 0 || n_total < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_batch_device: negative size");
+  if (n_cameras != 1 && n_cameras != 4) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_batch_device: n_cameras must be 1 or 4");
+  if (!ValidMode(mode)) return Fail(KMC_B200_ERR_BAD_MODE, "deskew_project_batch_device: unknown time mode");
+  if (!cameras || !uvzc_out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_project_batch_device: null camera / output table");
+  if (n_frames == 0 || n_total == 0) return KMC_B200_OK;
+  if (!in || !offsets_dev || !params_dev) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_project_batch_device: null argument");
+  if (!Aligned(in, 16) || (xyzi_out && !Aligned(xyzi_out, 16)) || !Aligned(params_dev, 16) || !Aligned(offsets_dev, 8))
+    return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_batch_device: misaligned buffer");
+  for (int c = 0; c < n_cameras; ++c) {
+    if (!uvzc_out[c]) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_project_batch_device: null pixel buffer");
+    if (!Aligned(uvzc_out[c], 16)) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_batch_device: misaligned pixel buffer");
+    if (uvzc_out[c] == in || uvzc_out[c] == xyzi_out) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_batch_device: a pixel buffer aliases a cloud");
+    for (int d = 0; d < c; ++d)
+      if (uvzc_out[c] == uvzc_out[d]) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_project_batch_device: pixel buffers must be distinct");
+  }
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewProjectBatch(in, xyzi_out, uvzc_out, n_cameras, offsets_dev, params_dev, n_frames, n_total, cameras, mode,
+                                                       sm, static_cast<cudaStream_t>(stream)));
+  return KMC_B200_OK;
+}
+
+int kmc_b200_deskew_cloud_f64_batch_device(const double* cloud, const double* stamps, double* out, const int64_t* offsets_dev,
+                                           const kmc_b200_frame_params* params_dev, const double* times_dev, int32_t n_frames,
+                                           int64_t n_total, int* flags_dev, void* stream) {
+  if (n_frames < 0 || n_total < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_cloud_f64_batch_device: negative size");
+  if (n_frames == 0) return KMC_B200_OK;
+  if (!offsets_dev || !params_dev || !times_dev || !flags_dev) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_batch_device: null table");
+  if (n_total > 0 && (!cloud || !stamps || !out)) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_batch_device: null buffer");
+  if (!Aligned(cloud, 8) || !Aligned(stamps, 8) || !Aligned(out, 8) || !Aligned(times_dev, 8) || !Aligned(offsets_dev, 8) ||
+      !Aligned(params_dev, 16) || !Aligned(flags_dev, 4))
+    return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_cloud_f64_batch_device: misaligned buffer");
+  int device = 0, sm = 0;
+  KMC_CUDA_TRY(cudaGetDevice(&device));
+  if (int rc = SmCount(device, &sm)) return rc;
+  KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewCloudF64Batch(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, n_total, flags_dev, sm,
+                                                        static_cast<cudaStream_t>(stream)));
   return KMC_B200_OK;
 }
 

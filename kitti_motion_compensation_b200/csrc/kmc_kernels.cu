@@ -21,6 +21,7 @@
 // Memory: the N x 4 float32 "x y z i" array is read once and written once (32 B/point), 128-bit or 256-bit
 // (sm_100 LDG.256/STG.256) accesses, fully coalesced, several independent loads in flight per thread, persistent grid
 // sized in multiples of the SM count.  HBM-bandwidth bound; no shared memory, no tensor cores (nothing to contract).
+#include "kmc_internal.hpp"
 #include "kmc_kernels.cuh"
 #include "kmc_point_math.cuh"
 
@@ -328,6 +329,77 @@ __global__ void __launch_bounds__(BLOCK)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Deskew + projection over a BATCH of frames — the loop body of GenerateProjectionVisualizationOfRun (handlers.cpp:67-92:
+// per frame one MotionCompensateFrame and four ProjectPointcloudOnImage) for a whole run in one launch.  Frames back to
+// back as for DeskewBatchKernel (global offset / record tables, work items cut at frame boundaries, one coalesced
+// 64-byte record fetch per warp and piece); the cameras are the same for every frame of a run and ride in the constant
+// bank.  16 B/point read, 16 B/point written per camera (+16 with the deskewed cloud).
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE, int NCAM, bool WRITE_CLOUD, int VEC, int BLOCK>
+__device__ __forceinline__ void ProjectRange(const float4* __restrict__ in, float4* __restrict__ cloud_out, const PixelPlanes4& pix,
+                                             int64_t a, int64_t b, const kmc_b200_frame_params& P, const Cameras4& K) {
+  int const tid = threadIdx.x;
+  auto one = [&](int64_t i) {
+    float4 const p = DeskewPoint<MODE>(LoadPoint<0>(in + i), P);
+    if constexpr (WRITE_CLOUD) StorePoint<0>(cloud_out + i, p);
+#pragma unroll
+    for (int c = 0; c < NCAM; ++c) StorePoint<0>(pix.plane[c] + i, ProjectPoint(p, K.cam[c]));
+  };
+  if constexpr (VEC == 2) {
+    if (a & 1) {  // 256-bit accesses need an even point index
+      if (tid == 0 && a < b) one(a);
+      a += 1;
+    }
+  }
+  constexpr int64_t kTile = static_cast<int64_t>(BLOCK) * VEC;
+  int64_t base = a;
+  for (; base + kTile <= b; base += kTile) {
+    if constexpr (VEC == 2) {
+      int64_t const i = base + 2 * tid;
+      Point2 v = LoadPoint2<0>(in + i);
+      v.a = DeskewPoint<MODE>(v.a, P);
+      v.b = DeskewPoint<MODE>(v.b, P);
+      if constexpr (WRITE_CLOUD) StorePoint2<0>(cloud_out + i, v);
+#pragma unroll
+      for (int c = 0; c < NCAM; ++c) {
+        Point2 r;
+        r.a = ProjectPoint(v.a, K.cam[c]);
+        r.b = ProjectPoint(v.b, K.cam[c]);
+        StorePoint2<0>(pix.plane[c] + i, r);
+      }
+    } else {
+      one(base + tid);
+    }
+  }
+  for (int64_t i = base + tid; i < b; i += BLOCK) one(i);
+}
+
+template <int MODE, int NCAM, bool WRITE_CLOUD, int VEC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+    DeskewProjectBatchKernel(const float4* __restrict__ in, float4* __restrict__ cloud_out, PixelPlanes4 const pix,
+                             const int64_t* __restrict__ offsets, const kmc_b200_frame_params* __restrict__ table, int n_frames,
+                             int64_t n, int64_t item_points, double frames_per_point, const __grid_constant__ Cameras4 K) {
+  int64_t const n_items = (n + item_points - 1) / item_points;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int64_t p0 = item * item_points;
+    int64_t const p1 = (p0 + item_points < n) ? (p0 + item_points) : n;
+    int f = LocateFrame(offsets, n_frames, p0, frames_per_point);
+    while (p0 < p1 && f < n_frames) {
+      int64_t const frame_end = __ldg(offsets + f + 1);
+      if (frame_end <= p0) {  // empty frame
+        ++f;
+        continue;
+      }
+      int64_t const seg_end = frame_end < p1 ? frame_end : p1;
+      kmc_b200_frame_params const P = LoadParamsWarpBroadcast(table, f);
+      ProjectRange<MODE, NCAM, WRITE_CLOUD, VEC, BLOCK>(in, cloud_out, pix, p0, seg_end, P, K);
+      p0 = seg_end;
+      ++f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The reference's own memory layout (motion_compensation.cpp:16-28): cloud and result are COLUMN-major N x 4 doubles
 // (Eigen::MatrixX4d), per-point stamps a separate double vector.  Used by the C++ mirror of MotionCompensateFrame so that
 // no host-side layout conversion is needed.  The displacement is computed in fp32 from the rounded coordinates and the
@@ -356,6 +428,57 @@ __global__ void __launch_bounds__(kBlockThreads)
     out[3 * n + i] = w;
   }
   if (bad) atomicOr(flags, bad);
+}
+
+// A BATCH of frames in the reference's layout: frame f owns the 4 N_f doubles at cloud + 4 offsets[f] (its own column-major
+// N_f x 4 matrix: x | y | z | w columns), the N_f stamps at stamps + offsets[f], and the same block of `out`.  Per-frame
+// records in the global table as for DeskewBatchKernel, per-frame times (t_start, t_end, t_req) in a table of three
+// doubles, per-frame flags (bit 0 stamp out of range, bit 1 some w != 1).  72 B/point.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+    DeskewCloudF64BatchKernel(const double* __restrict__ cloud, const double* __restrict__ stamps, double* __restrict__ out,
+                              const int64_t* __restrict__ offsets, const kmc_b200_frame_params* __restrict__ table,
+                              const double* __restrict__ times, int n_frames, int64_t n, int64_t item_points, double frames_per_point,
+                              int* __restrict__ flags) {
+  int64_t const n_items = (n + item_points - 1) / item_points;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int64_t p0 = item * item_points;
+    int64_t const p1 = (p0 + item_points < n) ? (p0 + item_points) : n;
+    int f = LocateFrame(offsets, n_frames, p0, frames_per_point);
+    while (p0 < p1 && f < n_frames) {
+      int64_t const frame_begin = __ldg(offsets + f);
+      int64_t const frame_end = __ldg(offsets + f + 1);
+      if (frame_end <= p0) {  // empty frame
+        ++f;
+        continue;
+      }
+      int64_t const seg_end = frame_end < p1 ? frame_end : p1;
+      kmc_b200_frame_params const P = LoadParamsWarpBroadcast(table, f);
+      double const t1 = __ldg(times + 3 * f), t2 = __ldg(times + 3 * f + 1), t_req = __ldg(times + 3 * f + 2);
+      double const duration = t2 - t1;
+      double const x_req = (t_req - t1) / duration;
+      int64_t const nf = frame_end - frame_begin;
+      const double* const c = cloud + 4 * frame_begin;
+      double* const o = out + 4 * frame_begin;
+      const double* const ts = stamps + frame_begin;
+      int bad = 0;
+      for (int64_t i = p0 - frame_begin + threadIdx.x; i < seg_end - frame_begin; i += BLOCK) {
+        double const x = __ldg(c + i), y = __ldg(c + nf + i), z = __ldg(c + 2 * nf + i), w = __ldg(c + 3 * nf + i);
+        double const t = __ldg(ts + i);
+        if (!(t >= t1 && t <= t2)) bad |= 1;
+        if (w != 1.0) bad |= 2;
+        float const s = static_cast<float>((t - t1) / duration - x_req);
+        float3 const d = DeskewDeltaW(static_cast<float>(x), static_cast<float>(y), static_cast<float>(z), static_cast<float>(w), s, P);
+        o[i] = x + static_cast<double>(d.x);
+        o[nf + i] = y + static_cast<double>(d.y);
+        o[2 * nf + i] = z + static_cast<double>(d.z);
+        o[3 * nf + i] = w;
+      }
+      if (bad) atomicOr(flags + f, bad);
+      p0 = seg_end;
+      ++f;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -670,31 +793,38 @@ void ApplyTuneEnv(LaunchConfig& cfg) {
 
 uint64_t LaunchCount() { return g_launches.load(std::memory_order_relaxed); }
 
-LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_count) {
-  // Defaults from the B200 sweeps (profiles/r01_sweep_*.log): one 256-bit load + one 256-bit store per thread per tile,
-  // plain ld/st, 9 CTAs x 128 threads per SM (1152 threads, 36 KB of loads in flight per SM), work items of 16 tiles
-  // (4096 points).  The optimum is sharp in resident threads per SM: 768 / 1024 / 1152 / 1280 / 1408 / 1536 threads
-  // measured 5.8 / 6.39 / 6.54 / 6.50 / 6.14 / 6.05 TB/s (interleaved A/B runs, profiles/r01_sweep_ab.log), and more
-  // bytes in flight per thread (2-4 loads) measured 5.9-6.1 TB/s — at the copy ceiling extra requests only lengthen
-  // the DRAM queues.
+LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_count, bool batch) {
+  // Defaults from the B200 sweeps.  Per thread: one 256-bit load + one 256-bit store per tile, plain ld/st, 128-thread CTAs
+  // (40 registers, up to 16 CTAs resident per SM).  Round 1 shipped a PERSISTENT grid of 9 CTAs per SM taking work items
+  // round-robin (6.49-6.55 TB/s on the headline batch); ncu then showed the SMs' active cycles spread by 8 % under that
+  // static split (sm__cycles_active min 84.5 K / max 92 K on the 10 M-point frame: SMs differ in their distance to the
+  // memory controllers), i.e. the launch waits for its slowest SM.  Handing work items to CTAs through the hardware
+  // scheduler instead — ONE CTA PER WORK ITEM, grid = number of items — removes that tail:
+  //   batch 4000 x 130 000 points, items of 16 tiles (4096 points)    6 715 GB/s  (persistent 9 x 128: 6 491; torch copy_: 6 668)
+  //   one 10 M-point frame, items of 1 tile                           6 415 GB/s back to back (persistent: 5 949)
+  //   one 100 M-point frame                                           6 855 GB/s (persistent: 6 272)
+  // (profiles/r02_frame_sizes.log, r02_batch_nonpersistent.log).  The batch kernel keeps items of 16 tiles because every item
+  // pays a frame lookup and a record fetch (1 / 2 / 4 / 16 tiles: 5 811 / 6 314 / 6 511 / 6 715 GB/s); the single-frame
+  // kernel has no per-item cost and takes one tile per CTA.  ctas_per_sm is the cap of the grid in CTAs per SM: 4096 means
+  // "never persistent below 600 K items", 9 restores round 1's shape (KMC_B200_TUNE ctas=9,item_tiles=16).
   LaunchConfig cfg;
   cfg.vec = 2;
   cfg.unroll = 1;
   cfg.hint = 0;
   cfg.block = 128;
-  cfg.ctas_per_sm = 9;
-  cfg.item_tiles = 16;
+  cfg.ctas_per_sm = 4096;
+  cfg.item_tiles = batch ? 16 : 1;
   cfg.bulk = 0;
   cfg.stages = 4;
-  // Mid-size inputs: keep >= 16 work items per resident CTA so the tail stays small; tiny inputs (latency bound):
-  // one tile per item and 128-bit accesses to spread over as many CTAs as possible.
+  // Mid-size batches: keep at least ~16 items per resident CTA slot (148 x 9) so that the scheduler has something to balance;
+  // tiny inputs (latency bound): 128-bit accesses to spread over as many CTAs as possible.
   int64_t const tile = static_cast<int64_t>(cfg.block) * cfg.unroll * cfg.vec;
-  int64_t const resident = static_cast<int64_t>(sm_count) * cfg.ctas_per_sm;
-  int64_t const tiles_per_cta = n_points / (resident * tile);
-  if (tiles_per_cta < 16 * cfg.item_tiles) {
-    int64_t const t = tiles_per_cta / 16;
+  int64_t const slots = static_cast<int64_t>(sm_count) * 9;
+  int64_t const tiles_per_slot = n_points / (slots * tile);
+  if (tiles_per_slot < 16 * cfg.item_tiles) {
+    int64_t const t = tiles_per_slot / 16;
     cfg.item_tiles = static_cast<int>(t < 1 ? 1 : t);
-    if (tiles_per_cta < 1) cfg.vec = 1;
+    if (tiles_per_slot < 1) cfg.vec = 1;
   }
   ApplyTuneEnv(cfg);
   if (!aligned32) cfg.vec = 1;
@@ -771,7 +901,7 @@ ProjectShape PickProjectShape(bool aligned32, int stores_per_thread, bool deskew
     find("pvec", &shape.vec);
   }
   if (shape.block != 128) shape.block = 256;
-  shape.ctas_per_sm = std::min(std::max(shape.ctas_per_sm, 1), 16);
+  shape.ctas_per_sm = std::min(std::max(shape.ctas_per_sm, 1), 65536);  // > 16: one CTA per tile, not persistent
   if (!aligned32 || shape.vec != 2) shape.vec = 1;
   return shape;
 }
@@ -863,13 +993,86 @@ cudaError_t LaunchProject4(const float* in, float* cloud_out, float* const pix_o
   return cudaGetLastError();
 }
 
+namespace {
+template <int MODE, int NCAM, bool WRITE_CLOUD>
+void LaunchProjectBatchT(const float4* in4, float4* cloud4, const PixelPlanes4& planes, const int64_t* offsets, const kmc_b200_frame_params* table,
+                         int32_t n_frames, int64_t n, const Cameras4& K, const ProjectShape& shape, int sm_count, cudaStream_t stream) {
+  int const item_tiles = std::max(1, kmc_b200::internal::TuneValue("pitem_tiles", 16));
+  int64_t const item_points = static_cast<int64_t>(shape.block) * shape.vec * item_tiles;
+  int64_t const n_items = (n + item_points - 1) / item_points;
+  unsigned const grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_items, static_cast<int64_t>(sm_count) * shape.ctas_per_sm)));
+  double const fpp = static_cast<double>(n_frames) / static_cast<double>(n);
+#define KMC_PB_CALL(V, B) \
+  DeskewProjectBatchKernel<MODE, NCAM, WRITE_CLOUD, V, B><<<grid, B, 0, stream>>>(in4, cloud4, planes, offsets, table, n_frames, n, item_points, fpp, K)
+  if (shape.vec == 2) {
+    if (shape.block == 128) KMC_PB_CALL(2, 128);
+    else KMC_PB_CALL(2, 256);
+  } else {
+    if (shape.block == 128) KMC_PB_CALL(1, 128);
+    else KMC_PB_CALL(1, 256);
+  }
+#undef KMC_PB_CALL
+}
+}  // namespace
+
+cudaError_t LaunchDeskewProjectBatch(const float* in, float* cloud_out, float* const pix_out[], int n_cameras, const int64_t* offsets_dev,
+                                     const kmc_b200_frame_params* params_dev, int32_t n_frames, int64_t n_points,
+                                     const kmc_b200_camera_params cameras[], int mode, int sm_count, cudaStream_t stream) {
+  if (n_points <= 0 || n_frames <= 0) return cudaSuccess;
+  Cameras4 K{};
+  PixelPlanes4 planes{};
+  bool aligned32 = (reinterpret_cast<uintptr_t>(in) % 32 == 0) && (!cloud_out || reinterpret_cast<uintptr_t>(cloud_out) % 32 == 0);
+  for (int c = 0; c < n_cameras; ++c) {
+    K.cam[c] = cameras[c];
+    planes.plane[c] = reinterpret_cast<float4*>(pix_out[c]);
+    aligned32 = aligned32 && (reinterpret_cast<uintptr_t>(pix_out[c]) % 32 == 0);
+  }
+  ProjectShape const shape = PickProjectShape(aligned32, n_cameras + (cloud_out ? 1 : 0), true);
+  auto const* in4 = reinterpret_cast<const float4*>(in);
+  auto* cloud4 = reinterpret_cast<float4*>(cloud_out);
+  bool const az = (mode == KMC_B200_TIME_FROM_AZIMUTH);
+#define KMC_PB_DISPATCH(NCAM)                                                                                                              \
+  if (cloud_out) {                                                                                                                         \
+    if (az) LaunchProjectBatchT<KMC_B200_TIME_FROM_AZIMUTH, NCAM, true>(in4, cloud4, planes, offsets_dev, params_dev, n_frames, n_points, K, shape, sm_count, stream); \
+    else LaunchProjectBatchT<KMC_B200_TIME_FROM_W, NCAM, true>(in4, cloud4, planes, offsets_dev, params_dev, n_frames, n_points, K, shape, sm_count, stream);          \
+  } else {                                                                                                                                 \
+    if (az) LaunchProjectBatchT<KMC_B200_TIME_FROM_AZIMUTH, NCAM, false>(in4, nullptr, planes, offsets_dev, params_dev, n_frames, n_points, K, shape, sm_count, stream); \
+    else LaunchProjectBatchT<KMC_B200_TIME_FROM_W, NCAM, false>(in4, nullptr, planes, offsets_dev, params_dev, n_frames, n_points, K, shape, sm_count, stream);          \
+  }
+  if (n_cameras == 1) { KMC_PB_DISPATCH(1) }
+  else { KMC_PB_DISPATCH(4) }
+#undef KMC_PB_DISPATCH
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchDeskewCloudF64Batch(const double* cloud, const double* stamps, double* out, const int64_t* offsets_dev,
+                                      const kmc_b200_frame_params* params_dev, const double* times_dev, int32_t n_frames, int64_t n_points,
+                                      int* flags_dev, int sm_count, cudaStream_t stream) {
+  if (n_frames <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(flags_dev, 0, static_cast<size_t>(n_frames) * sizeof(int), stream);
+  if (e != cudaSuccess || n_points <= 0) return e;
+  int const block = kmc_b200::internal::TuneValue("f64_block", 256) == 128 ? 128 : 256;
+  int const ctas = std::max(kmc_b200::internal::TuneValue("f64_ctas", 6), 1);
+  int64_t const item_points = static_cast<int64_t>(block) * std::max(1, kmc_b200::internal::TuneValue("f64_item_tiles", 16));
+  int64_t const n_items = (n_points + item_points - 1) / item_points;
+  unsigned const grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_items, static_cast<int64_t>(sm_count) * ctas)));
+  double const fpp = static_cast<double>(n_frames) / static_cast<double>(n_points);
+  if (block == 128)
+    DeskewCloudF64BatchKernel<128><<<grid, 128, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, n_points, item_points, fpp, flags_dev);
+  else
+    DeskewCloudF64BatchKernel<256><<<grid, 256, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, n_points, item_points, fpp, flags_dev);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
 cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, double start, double end, int sm_count,
                                    cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   bool const vec2 = (reinterpret_cast<uintptr_t>(in) % 32 == 0) && (reinterpret_cast<uintptr_t>(stamps) % 16 == 0);
   int64_t const per_cta = static_cast<int64_t>(kStampBlockThreads) * (vec2 ? 2 : 1);
   int64_t grid = (n + per_cta - 1) / per_cta;
-  int64_t const cap = static_cast<int64_t>(sm_count) * 9;  // 1152 resident threads per SM, as the deskew kernel
+  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("stamp_ctas", 9));
   if (grid > cap) grid = cap;
   auto const* in4 = reinterpret_cast<const float4*>(in);
   if (vec2) PseudoTimeStampsKernel<true><<<static_cast<unsigned>(grid), kStampBlockThreads, 0, stream>>>(in4, stamps, n, start, end - start);
@@ -882,7 +1085,7 @@ cudaError_t LaunchDeskewCloudF64(const double* cloud, const double* stamps, doub
                                  const kmc_b200_frame_params& params, int* flags_dev, int sm_count, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
-  int64_t const cap = static_cast<int64_t>(sm_count) * 6;
+  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("f64_ctas", 6));
   if (grid > cap) grid = cap;
   DeskewCloudF64Kernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(cloud, stamps, out, n, t1, t2, x_req, params, flags_dev);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -908,7 +1111,7 @@ cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* s
                                      int sm_count, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
-  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("stamp_ctas", 8));
   if (grid > cap) grid = cap;
   PseudoTimeStampsXyKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(x, y, stamps, n, start, end - start);
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -15,7 +15,7 @@ struct LaunchConfig {
   int unroll;      // memory instructions in flight per thread per tile (1, 2)
   int hint;        // 0 = plain ld/st, 1 = L1::no_allocate (+ .nc load)
   int block;       // threads per CTA (128, 256, 512)
-  int ctas_per_sm; // persistent grid = SMs * ctas_per_sm (capped by the number of work items)
+  int ctas_per_sm; // grid = min(work items, SMs * ctas_per_sm): <= 16 makes the grid persistent, the default (4096) one CTA per item
   int item_tiles;  // tiles per work item (a work item is the unit a CTA takes per scheduling step)
   int bulk;        // 1 = single-frame kernel variant staged through shared memory by the TMA engine (kmc_kernels_bulk.cu);
                    //     `unroll` then means points per thread per stage (2, 4, 8)
@@ -24,7 +24,8 @@ struct LaunchConfig {
 
 constexpr int kBlockThreads = 256;
 
-LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_count);
+// batch: the launch is LaunchDeskewBatch (work items pay a frame lookup) rather than LaunchDeskewFrame.
+LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_count, bool batch);
 
 cudaError_t LaunchDeskewFrame(const float* in, float* out, int64_t n, const kmc_b200_frame_params& params, int mode,
                               const LaunchConfig& cfg, int sm_count, cudaStream_t stream);
@@ -59,6 +60,18 @@ cudaError_t LaunchProject4(const float* in, float* cloud_out, float* const pix_o
 // Deskew in the reference's own layout: column-major N x 4 double cloud + per-point double stamps -> column-major double.
 cudaError_t LaunchDeskewCloudF64(const double* cloud, const double* stamps, double* out, int64_t n, double t1, double t2, double x_req,
                                  const kmc_b200_frame_params& params, int* flags_dev, int sm_count, cudaStream_t stream);
+
+// Deskew + projection onto n_cameras (1 or 4) cameras over a batch of frames (tables in device memory as for LaunchDeskewBatch);
+// cloud_out may be nullptr.
+cudaError_t LaunchDeskewProjectBatch(const float* in, float* cloud_out, float* const pix_out[], int n_cameras, const int64_t* offsets_dev,
+                                     const kmc_b200_frame_params* params_dev, int32_t n_frames, int64_t n_points,
+                                     const kmc_b200_camera_params cameras[], int mode, int sm_count, cudaStream_t stream);
+
+// A batch of frames in the reference's column-major double layout (frame f: 4 N_f doubles at cloud + 4 offsets[f]); times_dev holds
+// (t_start, t_end, t_req) per frame, flags_dev one int per frame (zeroed by the call).
+cudaError_t LaunchDeskewCloudF64Batch(const double* cloud, const double* stamps, double* out, const int64_t* offsets_dev,
+                                      const kmc_b200_frame_params* params_dev, const double* times_dev, int32_t n_frames, int64_t n_points,
+                                      int* flags_dev, int sm_count, cudaStream_t stream);
 
 // Narrow transport of the reference-layout host path: float columns x | y | z | s [| w] of stride_points entries each
 // (a multiple of 4, 16-byte aligned) -> float columns dx | dy | dz.

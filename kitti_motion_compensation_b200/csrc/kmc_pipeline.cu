@@ -140,7 +140,8 @@ int EnsureTables(kmc_b200_handle* h, int64_t n_frames) {
 // zero_copy: no copy engines — the kernel reads the pinned source and writes the pinned sink directly over PCIe (one launch
 // per chunk).  For a transfer of a few MB the two copies' fixed latencies (~10 us each) and their serialisation behind the
 // kernel cost more than SM-issued PCIe reads lose: one 130 000-point scan takes 67 us instead of 96 us
-// (profiles/r02_latency_probe.log); from ~1 M points on the copy engines win (47 vs 40 GB/s each way).
+// (profiles/r02_latency_probe.log), a 2 M-point frame 881 us instead of 978 us (profiles/r02_sweep_single_scan.log); for long
+// streams the copy engines are at least as fast (36-47 vs 36-40 GB/s each way, box dependent) and leave the SMs free.
 template <class Fetch, class Launch, class Sink, class Deliver>
 int StreamChunksImpl(kmc_b200_handle* h, int64_t n, bool zero_copy, Fetch&& fetch, Launch&& launch, Sink&& sink, Deliver&& deliver);
 
@@ -290,12 +291,12 @@ int StreamChunksImpl(kmc_b200_handle* h, int64_t n, bool zero_copy, Fetch&& fetc
 }
 
 // A host ARRAY through the device: pinned caller memory is used directly, pageable memory is staged through the slots;
-// small transfers (<= zc_points, default 400 000 points = 6.4 MB each way) skip the copy engines (zero_copy above).
+// transfers of up to zc_points (default 2 000 000 points = 32 MB each way) skip the copy engines (zero_copy above).
 template <class Launch>
 int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t n, Launch&& launch) {
   bool const in_pinned = IsPinnedHost(in);
   bool const out_pinned = IsPinnedHost(out);
-  bool zero_copy = n <= TuneValue("zc_points", 400000);
+  bool zero_copy = n <= TuneValue("zc_points", 2000000);
   if (zero_copy && in_pinned) {
     const float* alias = nullptr;
     zero_copy = DeviceAlias(in, &alias);
@@ -324,9 +325,9 @@ int StreamThroughDevice(kmc_b200_handle* h, const float* in, float* out, int64_t
 // Launch shape of a chunk of a host call: the HBM-tuned shape when the chunk sits in device memory; when the kernel reads
 // pinned host memory over PCIe (zero copy) what matters is the number of read requests in flight on the link, not HBM
 // queues: one CTA of 256 threads per SM, 128-bit accesses (KMC_B200_TUNE zc_block / zc_ctas / zc_vec / zc_tiles).
-kmc_b200::dev::LaunchConfig PickHostCallConfig(const kmc_b200_handle* h, int64_t count, const float* src, const float* dst) {
+kmc_b200::dev::LaunchConfig PickHostCallConfig(const kmc_b200_handle* h, int64_t count, const float* src, const float* dst, bool batch) {
   bool const aligned32 = Aligned(src, 32) && Aligned(dst, 32);
-  auto cfg = kmc_b200::dev::PickConfig(count, aligned32, false, h->sm_count);
+  auto cfg = kmc_b200::dev::PickConfig(count, aligned32, false, h->sm_count, batch);
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
     cfg.bulk = 0;
@@ -436,7 +437,7 @@ int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, 
   KMC_CUDA_TRY(guard.status());
   kmc_b200_frame_params const P = *params;
   return StreamThroughDevice(h, in, out, n, [&](int slot, int64_t, int64_t count, const float* src, float* dst) -> int {
-    auto const cfg = PickHostCallConfig(h, count, src, dst);
+    auto const cfg = PickHostCallConfig(h, count, src, dst, false);
     KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(src, dst, count, P, mode, cfg, h->sm_count, h->stream[slot]));
     return KMC_B200_OK;
   });
@@ -464,7 +465,7 @@ int kmc_b200_deskew_batch_host(kmc_b200_handle* h, const float* in, float* out, 
   KMC_CUDA_TRY(cudaMemcpyAsync(h->d_params, params, static_cast<size_t>(n_frames) * sizeof(kmc_b200_frame_params), cudaMemcpyHostToDevice, h->stream[0]));
   KMC_CUDA_TRY(cudaStreamSynchronize(h->stream[0]));
   return StreamThroughDevice(h, in, out, n_total, [&](int slot, int64_t first, int64_t count, const float* src, float* dst) -> int {
-    auto const cfg = PickHostCallConfig(h, count, src, dst);
+    auto const cfg = PickHostCallConfig(h, count, src, dst, true);
     KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(src, dst, h->d_offsets, h->d_params, n_frames, count, first, n_total, mode, cfg,
                                                   h->sm_count, h->stream[slot]));
     return KMC_B200_OK;
@@ -558,35 +559,31 @@ int64_t F64ChunkPoints(int64_t n) {
 //                          stamps checked against [t_start, t_end]                       -> pinned staging
 //   H2D 16 B/point -> DeskewDeltaColumnsKernel -> D2H 12 B/point                          (slot's stream)
 //   pass 2 (host threads)  out = x + double(dx), ...                                      <- pinned staging
-// in chunks over three slots, so the host passes of one chunk run while the link and the GPU work on the others.
-int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, const double* stamps, double* out, int64_t n, double t_start,
-                                   double t_end, double t_req, const kmc_b200_frame_params* params, int* flags_out) try {
-  TraceRange const trace("kmc_b200_deskew_cloud_f64_host");
-  if (flags_out) *flags_out = 0;
-  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null handle");
-  if (n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_cloud_f64_host: negative n_points");
-  if (!params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null params");
-  if (!(t_end > t_start)) return Fail(KMC_B200_ERR_EMPTY_INTERVAL, "deskew_cloud_f64_host: t_end <= t_start");
-  if (!(t_req >= t_start && t_req <= t_end)) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "deskew_cloud_f64_host: requested time outside [t_start, t_end]");
-  if (n == 0) return KMC_B200_OK;
-  if (!cloud || !stamps || !out) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null buffer");
-  std::lock_guard<std::mutex> lock(h->mu);
-  DeviceGuard const guard(h->device);
-  KMC_CUDA_TRY(guard.status());
+// in chunks over three slots, so the host passes of one chunk run while the link and the GPU work on the others.  The
+// chunk sequence runs across ALL frames of a call without draining in between.
+extern "C++" {
+namespace {
+
+struct F64Frame {
+  const double* cloud;
+  const double* stamps;
+  double* out;
+  int64_t n;
+  double t_start, t_end, t_req;
+  kmc_b200_frame_params P;
+  int flags;
+};
+
+int F64HostPipeline(kmc_b200_handle* h, F64Frame* frames, int32_t n_frames) {
   constexpr int kSlots = kmc_b200_handle::kSlots;
   constexpr int64_t kBlock = 4096;  // points per host task
-  int64_t const chunk = F64ChunkPoints(n);
-  if (int rc = EnsureF64Staging(h, chunk)) return rc;
-  kmc_b200_frame_params const P = *params;
-  double const duration = t_end - t_start;
-  double const x_req = (t_req - t_start) / duration;
-  const double* const X = cloud;
-  const double* const Y = cloud + n;
-  const double* const Z = cloud + 2 * n;
-  const double* const W = cloud + 3 * n;
+  int64_t longest = 0;
+  for (int32_t f = 0; f < n_frames; ++f) longest = std::max(longest, frames[f].n);
+  if (longest == 0) return KMC_B200_OK;
+  if (int rc = EnsureF64Staging(h, F64ChunkPoints(longest))) return rc;
   size_t const slot_floats = 8 * static_cast<size_t>(h->f64_chunk);
-  std::atomic<int> flags{0};
   struct Pending {
+    int32_t frame = 0;
     int64_t first = 0, count = 0;
     bool active = false;
   } pending[kSlots];
@@ -594,7 +591,12 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
   auto retire = [&](int slot) -> int {
     if (!pending[slot].active) return KMC_B200_OK;
     KMC_CUDA_TRY(cudaEventSynchronize(h->done[slot]));
-    int64_t const first = pending[slot].first, count = pending[slot].count, stride = (count + 3) & ~int64_t{3};
+    F64Frame const& fr = frames[pending[slot].frame];
+    int64_t const n = fr.n, first = pending[slot].first, count = pending[slot].count, stride = (count + 3) & ~int64_t{3};
+    const double* const X = fr.cloud;
+    const double* const Y = fr.cloud + n;
+    const double* const Z = fr.cloud + 2 * n;
+    double* const out = fr.out;
     const float* const d = h->f64_pinned + slot * slot_floats + 5 * static_cast<size_t>(h->f64_chunk);
     SharedPool::Run((count + kBlock - 1) / kBlock, [=](int64_t b) {
       int64_t const i1 = std::min(count, (b + 1) * kBlock);
@@ -606,8 +608,20 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
     return KMC_B200_OK;
   };
 
-  auto body = [&]() -> int {
-    int64_t k = 0;
+  int64_t k = 0;  // chunk counter across all frames
+  for (int32_t f = 0; f < n_frames; ++f) {
+    F64Frame& fr = frames[f];
+    int64_t const n = fr.n;
+    if (n == 0) continue;
+    int64_t const chunk = std::min(F64ChunkPoints(n), h->f64_chunk);
+    double const t_start = fr.t_start, t_end = fr.t_end, duration = fr.t_end - fr.t_start;
+    double const x_req = (fr.t_req - fr.t_start) / duration;
+    const double* const X = fr.cloud;
+    const double* const Y = fr.cloud + n;
+    const double* const Z = fr.cloud + 2 * n;
+    const double* const W = fr.cloud + 3 * n;
+    const double* const stamps = fr.stamps;
+    double* const out = fr.out;
     for (int64_t first = 0; first < n; first += chunk, ++k) {
       int const slot = static_cast<int>(k % kSlots);
       if (int rc = retire(slot)) return rc;
@@ -638,7 +652,7 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
         if (outside | not_one) chunk_flags.fetch_or((outside ? 1 : 0) | (not_one ? 2 : 0), std::memory_order_relaxed);
       });
       int const cf = chunk_flags.load(std::memory_order_relaxed);
-      flags.fetch_or(cf, std::memory_order_relaxed);
+      fr.flags |= cf;
       bool const has_w = (cf & 2) != 0;
       if (has_w) {  // rare: a non-homogeneous 4th column travels as a fifth float column
         SharedPool::Run((stride + kBlock - 1) / kBlock, [=](int64_t b) {
@@ -648,30 +662,86 @@ int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, cons
       }
       cudaStream_t const st = h->stream[slot];
       KMC_CUDA_TRY(cudaMemcpyAsync(d_up, up, static_cast<size_t>(has_w ? 5 : 4) * stride * sizeof(float), cudaMemcpyHostToDevice, st));
-      KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewDeltaColumns(d_up, d_down, stride, has_w, P, h->sm_count, st));
+      KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewDeltaColumns(d_up, d_down, stride, has_w, fr.P, h->sm_count, st));
       KMC_CUDA_TRY(cudaMemcpyAsync(up + 5 * static_cast<size_t>(h->f64_chunk), d_down, static_cast<size_t>(3) * stride * sizeof(float),
                                    cudaMemcpyDeviceToHost, st));
       KMC_CUDA_TRY(cudaEventRecord(h->done[slot], st));
-      pending[slot] = {first, count, true};
+      pending[slot] = {f, first, count, true};
     }
-    for (int j = 0; j < kSlots; ++j)
-      if (int rc = retire(static_cast<int>((k + j) % kSlots))) return rc;  // oldest first
-    return KMC_B200_OK;
-  };
-  int const rc = body();
+  }
+  for (int j = 0; j < kSlots; ++j)
+    if (int rc = retire(static_cast<int>((k + j) % kSlots))) return rc;  // oldest first
+  return KMC_B200_OK;
+}
+
+// Validates one frame's arguments (status as the single-frame call) — everything is checked before anything is launched.
+int F64CheckFrame(const char* who, const F64Frame& fr) {
+  if (fr.n < 0) return Fail(KMC_B200_ERR_BAD_SIZE, std::string(who) + ": negative n_points");
+  if (!(fr.t_end > fr.t_start)) return Fail(KMC_B200_ERR_EMPTY_INTERVAL, std::string(who) + ": t_end <= t_start");
+  if (!(fr.t_req >= fr.t_start && fr.t_req <= fr.t_end))
+    return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, std::string(who) + ": requested time outside [t_start, t_end]");
+  if (fr.n > 0 && (!fr.cloud || !fr.stamps || !fr.out)) return Fail(KMC_B200_ERR_NULL_POINTER, std::string(who) + ": null buffer");
+  return KMC_B200_OK;
+}
+
+int F64RunLocked(kmc_b200_handle* h, F64Frame* frames, int32_t n_frames) {
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard const guard(h->device);
+  KMC_CUDA_TRY(guard.status());
+  int const rc = F64HostPipeline(h, frames, n_frames);
   if (rc != KMC_B200_OK) {  // no copy may still touch the staging buffers once the call has reported an error
     std::string const keep = LastError();
-    for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
+    for (int s = 0; s < kmc_b200_handle::kSlots; ++s) cudaStreamSynchronize(h->stream[s]);
     cudaGetLastError();
     LastError() = keep;
-    return rc;
   }
-  int const f = flags.load(std::memory_order_relaxed);
-  if (flags_out) *flags_out = f;
-  if (f & 1) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "a point stamp lies outside [t_start, t_end] (reference asserts, trajectory_interpolation.cpp:32)");
+  return rc;
+}
+
+}  // namespace
+}  // extern "C++"
+
+int kmc_b200_deskew_cloud_f64_host(kmc_b200_handle* h, const double* cloud, const double* stamps, double* out, int64_t n, double t_start,
+                                   double t_end, double t_req, const kmc_b200_frame_params* params, int* flags_out) try {
+  TraceRange const trace("kmc_b200_deskew_cloud_f64_host");
+  if (flags_out) *flags_out = 0;
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null handle");
+  if (!params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_host: null params");
+  F64Frame frame{cloud, stamps, out, n, t_start, t_end, t_req, *params, 0};
+  if (int rc = F64CheckFrame("deskew_cloud_f64_host", frame)) return rc;
+  if (n == 0) return KMC_B200_OK;
+  if (int rc = F64RunLocked(h, &frame, 1)) return rc;
+  if (flags_out) *flags_out = frame.flags;
+  if (frame.flags & 1) return Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "a point stamp lies outside [t_start, t_end] (reference asserts, trajectory_interpolation.cpp:32)");
   return KMC_B200_OK;
 }
 KMC_CATCH_AT_BOUNDARY("deskew_cloud_f64_host")
+
+int kmc_b200_deskew_cloud_f64_batch_host(kmc_b200_handle* h, const double* const* clouds, const double* const* stamps, double* const* outs,
+                                         const int64_t* n_points, const double* times, const kmc_b200_frame_params* params,
+                                         int32_t n_frames, int* flags_out) try {
+  TraceRange const trace("kmc_b200_deskew_cloud_f64_batch_host");
+  if (!h) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_batch_host: null handle");
+  if (n_frames < 0) return Fail(KMC_B200_ERR_BAD_SIZE, "deskew_cloud_f64_batch_host: negative n_frames");
+  if (n_frames == 0) return KMC_B200_OK;
+  if (!clouds || !stamps || !outs || !n_points || !times || !params) return Fail(KMC_B200_ERR_NULL_POINTER, "deskew_cloud_f64_batch_host: null table");
+  std::vector<F64Frame> frames(static_cast<size_t>(n_frames));
+  for (int32_t f = 0; f < n_frames; ++f) {
+    frames[static_cast<size_t>(f)] = F64Frame{clouds[f], stamps[f], outs[f], n_points[f], times[3 * f], times[3 * f + 1], times[3 * f + 2], params[f], 0};
+    if (flags_out) flags_out[f] = 0;
+    if (int rc = F64CheckFrame("deskew_cloud_f64_batch_host", frames[static_cast<size_t>(f)]))
+      return Fail(rc, "frame " + std::to_string(f) + ": " + LastError());
+  }
+  if (int rc = F64RunLocked(h, frames.data(), n_frames)) return rc;
+  int status = KMC_B200_OK;
+  for (int32_t f = 0; f < n_frames; ++f) {
+    if (flags_out) flags_out[f] = frames[static_cast<size_t>(f)].flags;
+    if ((frames[static_cast<size_t>(f)].flags & 1) && status == KMC_B200_OK)
+      status = Fail(KMC_B200_ERR_TIME_OUT_OF_RANGE, "frame " + std::to_string(f) + ": a point stamp lies outside [t_start, t_end] (reference asserts, trajectory_interpolation.cpp:32)");
+  }
+  return status;
+}
+KMC_CATCH_AT_BOUNDARY("deskew_cloud_f64_batch_host")
 
 int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n, double start, double end,
                                         double* stamps) try {
@@ -865,7 +935,7 @@ int kmc_b200_deskew_bin_file(kmc_b200_handle* h, const char* path_in, const char
   KMC_CUDA_TRY(guard.status());
   kmc_b200_frame_params const P = *params;
   int const rc = StreamBinFile(h, path_in, path_out, n, [&](int slot, int64_t, int64_t count, const float* src, float* dst) -> int {
-    auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
+    auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count, false);
     KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewFrame(src, dst, count, P, KMC_B200_TIME_FROM_AZIMUTH, cfg, h->sm_count, h->stream[slot]));
     return KMC_B200_OK;
   });
@@ -1014,7 +1084,7 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
       }
       size_t const f = static_cast<size_t>(grp.first_file);
       status = StreamBinFile(h, paths_in[f], paths_out[f], count, [&](int s, int64_t first, int64_t chunk, const float* src, float* dst) -> int {
-        auto const cfg = kmc_b200::dev::PickConfig(chunk, true, false, h->sm_count);
+        auto const cfg = kmc_b200::dev::PickConfig(chunk, true, false, h->sm_count, true);
         KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(src, dst, h->d_offsets, h->d_params, n_files, chunk, base + first, n_total, mode, cfg,
                                                       h->sm_count, h->stream[s]));
         return KMC_B200_OK;
@@ -1030,7 +1100,7 @@ int kmc_b200_deskew_bin_files(kmc_b200_handle* h, int32_t n_files, const char* c
       if (count > 0) {
         size_t const bytes = static_cast<size_t>(count) * 16;
         KMC_CUDA_TRY(cudaMemcpyAsync(h->d_in[slot], h->h_in[slot], bytes, cudaMemcpyHostToDevice, h->stream[slot]));
-        auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count);
+        auto const cfg = kmc_b200::dev::PickConfig(count, true, false, h->sm_count, true);
         KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewBatch(h->d_in[slot], h->d_out[slot], h->d_offsets, h->d_params, n_files, count, base,
                                                       n_total, mode, cfg, h->sm_count, h->stream[slot]));
         KMC_CUDA_TRY(cudaMemcpyAsync(h->h_out[slot], h->d_out[slot], bytes, cudaMemcpyDeviceToHost, h->stream[slot]));

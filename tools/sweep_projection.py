@@ -74,7 +74,7 @@ def main():
     best = {}
     print("shape                  " + "".join(f"{name:>24s}" for name, _, _ in kernels), flush=True)
     for block, c, v in itertools.product(blocks, ctas, vecs):
-        if block * c > 2048:
+        if block * c > 2048 and c <= 16:  # c > 16: one CTA per tile (not persistent), residency is the hardware's business
             continue
         os.environ["KMC_B200_TUNE"] = f"pblock={block},pctas={c},pvec={v}"
         row = []

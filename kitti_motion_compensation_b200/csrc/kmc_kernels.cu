@@ -800,11 +800,12 @@ LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_
   // static split (sm__cycles_active min 84.5 K / max 92 K on the 10 M-point frame: SMs differ in their distance to the
   // memory controllers), i.e. the launch waits for its slowest SM.  Handing work items to CTAs through the hardware
   // scheduler instead — ONE CTA PER WORK ITEM, grid = number of items — removes that tail:
-  //   batch 4000 x 130 000 points, items of 16 tiles (4096 points)    6 715 GB/s  (persistent 9 x 128: 6 491; torch copy_: 6 668)
+  //   batch 4000 x 130 000 points, items of 8 tiles (2048 points)     6 826 GB/s  (persistent 9 x 128: 6 558; torch copy_: 6 668)
   //   one 10 M-point frame, items of 1 tile                           6 415 GB/s back to back (persistent: 5 949)
   //   one 100 M-point frame                                           6 855 GB/s (persistent: 6 272)
-  // (profiles/r02_frame_sizes.log, r02_batch_nonpersistent.log).  The batch kernel keeps items of 16 tiles because every item
-  // pays a frame lookup and a record fetch (1 / 2 / 4 / 16 tiles: 5 811 / 6 314 / 6 511 / 6 715 GB/s); the single-frame
+  // (profiles/r02_frame_sizes.log, r02_batch_nonpersistent.log, r02_batch_items.log).  The batch kernel takes items of 8 tiles
+  // because every item pays a frame lookup and a record fetch (1 / 2 / 4 / 8 / 16 / 32 / 64 tiles: 5 811 / 6 314 / 6 511 / 6 826 /
+  // 6 724 / 6 650 / 6 609 GB/s); the single-frame
   // kernel has no per-item cost and takes one tile per CTA.  ctas_per_sm is the cap of the grid in CTAs per SM: 4096 means
   // "never persistent below 600 K items", 9 restores round 1's shape (KMC_B200_TUNE ctas=9,item_tiles=16).
   LaunchConfig cfg;
@@ -813,7 +814,7 @@ LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_
   cfg.hint = 0;
   cfg.block = 128;
   cfg.ctas_per_sm = 4096;
-  cfg.item_tiles = batch ? 16 : 1;
+  cfg.item_tiles = batch ? 8 : 1;
   cfg.bulk = 0;
   cfg.stages = 4;
   // Mid-size batches: keep at least ~16 items per resident CTA slot (148 x 9) so that the scheduler has something to balance;
@@ -821,8 +822,8 @@ LaunchConfig PickConfig(int64_t n_points, bool aligned32, bool in_place, int sm_
   int64_t const tile = static_cast<int64_t>(cfg.block) * cfg.unroll * cfg.vec;
   int64_t const slots = static_cast<int64_t>(sm_count) * 9;
   int64_t const tiles_per_slot = n_points / (slots * tile);
-  if (tiles_per_slot < 16 * cfg.item_tiles) {
-    int64_t const t = tiles_per_slot / 16;
+  if (tiles_per_slot < 32 * cfg.item_tiles) {
+    int64_t const t = tiles_per_slot / 32;
     cfg.item_tiles = static_cast<int>(t < 1 ? 1 : t);
     if (tiles_per_slot < 1) cfg.vec = 1;
   }
@@ -868,25 +869,26 @@ cudaError_t LaunchDeskewBatch(const float* in, float* out, const int64_t* offset
 }
 
 namespace {
-// Launch shape of the projection kernels: threads per CTA, resident CTAs per SM (persistent grid) and 128- vs 256-bit
-// accesses; KMC_B200_TUNE="pblock=128,pctas=9,pvec=2" overrides the defaults for tools/sweep_projection.py.
-// Defaults from the B200 sweep (profiles/r01_sweep_projection.log, 100 M points): the best number of resident threads per
-// SM falls as the stores per thread rise, i.e. what is held constant is the memory traffic in flight per SM —
-//   1 load + 1 store  (project only)            128 x 8   6 570 GB/s   (5 x 256: 6 017)
-//   1 load + 1 store  (deskew + project)        256 x 5   6 377        (more arithmetic per point, wants more warps)
-//   1 load + 2 stores (deskew + project + cloud) 128 x 6   6 391        (5 x 256: 5 825)
-//   1 load + 4 stores (four cameras)            128 x 5   6 270        (5 x 256, 128-bit: 5 354)
-//   1 load + 5 stores (four cameras + cloud)    128 x 5   5 997        (5 x 256, 128-bit: 5 296)
+// Launch shape of the projection kernels: threads per CTA, cap of the grid in CTAs per SM and 128- vs 256-bit accesses;
+// KMC_B200_TUNE="pblock=128,pctas=9,pvec=2" overrides the defaults for tools/sweep_projection.py.
+// Round 1 shipped persistent grids whose best residency fell as the stores per thread rose (8 / 5 / 6 / 5 / 5 CTAs per SM).
+// As for the deskew kernels, ONE CTA PER TILE — the hardware scheduler balancing SMs of different speed — beats every
+// persistent shape (profiles/r02_sweep_projection.log, 100 M points, torch copy_ 6 550, fill_ 7 166 GB/s on that box):
+//   1 load + 1 store  (project only)             128 threads   6 939 GB/s   (persistent 8 x 128: 6 611)
+//   1 load + 1 store  (deskew + project)         128           6 686        (persistent 5 x 256: 6 371)
+//   1 load + 2 stores (deskew + project + cloud) 128           6 854        (persistent 6 x 128: 6 335)
+//   1 load + 4 stores (four cameras)             128 / 256     6 714 / 6 723 (persistent 5 x 128: 6 244)
+//   1 load + 5 stores (four cameras + cloud)     128 / 256     6 669 / 6 678 (persistent 5 x 128: 6 171)
 struct ProjectShape {
   int block = 128;
-  int ctas_per_sm = 8;
+  int ctas_per_sm = 65536;
   int vec = 2;
 };
 
 ProjectShape PickProjectShape(bool aligned32, int stores_per_thread, bool deskew) {
   ProjectShape shape;
-  shape.ctas_per_sm = stores_per_thread >= 4 ? 5 : stores_per_thread == 2 ? 6 : deskew ? 5 : 8;
-  if (deskew && stores_per_thread == 1) shape.block = 256;
+  (void)stores_per_thread;
+  (void)deskew;
   if (const char* env = std::getenv("KMC_B200_TUNE")) {
     auto find = [&](const char* key, int* out) {
       size_t const len = std::strlen(key);
@@ -997,7 +999,7 @@ namespace {
 template <int MODE, int NCAM, bool WRITE_CLOUD>
 void LaunchProjectBatchT(const float4* in4, float4* cloud4, const PixelPlanes4& planes, const int64_t* offsets, const kmc_b200_frame_params* table,
                          int32_t n_frames, int64_t n, const Cameras4& K, const ProjectShape& shape, int sm_count, cudaStream_t stream) {
-  int const item_tiles = std::max(1, kmc_b200::internal::TuneValue("pitem_tiles", 16));
+  int const item_tiles = std::max(1, kmc_b200::internal::TuneValue("pitem_tiles", 8));
   int64_t const item_points = static_cast<int64_t>(shape.block) * shape.vec * item_tiles;
   int64_t const n_items = (n + item_points - 1) / item_points;
   unsigned const grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_items, static_cast<int64_t>(sm_count) * shape.ctas_per_sm)));
@@ -1072,7 +1074,7 @@ cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, d
   bool const vec2 = (reinterpret_cast<uintptr_t>(in) % 32 == 0) && (reinterpret_cast<uintptr_t>(stamps) % 16 == 0);
   int64_t const per_cta = static_cast<int64_t>(kStampBlockThreads) * (vec2 ? 2 : 1);
   int64_t grid = (n + per_cta - 1) / per_cta;
-  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("stamp_ctas", 9));
+  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("stamp_ctas", 4096));  // one CTA per tile: 7 170 GB/s vs 6 289 persistent (24 B/point, profiles/r02_sweep_secondary.log)
   if (grid > cap) grid = cap;
   auto const* in4 = reinterpret_cast<const float4*>(in);
   if (vec2) PseudoTimeStampsKernel<true><<<static_cast<unsigned>(grid), kStampBlockThreads, 0, stream>>>(in4, stamps, n, start, end - start);
@@ -1085,7 +1087,8 @@ cudaError_t LaunchDeskewCloudF64(const double* cloud, const double* stamps, doub
                                  const kmc_b200_frame_params& params, int* flags_dev, int sm_count, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
-  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("f64_ctas", 6));
+  // 8 x 256 threads per SM (full residency): 6 587 GB/s; 6 x 256: 5 886; one CTA per tile: 6 258 (profiles/r02_sweep_secondary.log)
+  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("f64_ctas", 8));
   if (grid > cap) grid = cap;
   DeskewCloudF64Kernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(cloud, stamps, out, n, t1, t2, x_req, params, flags_dev);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1111,7 +1114,7 @@ cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* s
                                      int sm_count, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
-  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("stamp_ctas", 8));
+  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("stamp_ctas", 6));  // FP64-heavy: 6 x 256 threads per SM 5 387 GB/s, 8 x 256 4 310, one CTA per tile 3 646
   if (grid > cap) grid = cap;
   PseudoTimeStampsXyKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(x, y, stamps, n, start, end - start);
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -434,8 +434,8 @@ __global__ void __launch_bounds__(kBlockThreads)
 // N_f x 4 matrix: x | y | z | w columns), the N_f stamps at stamps + offsets[f], and the same block of `out`.  Per-frame
 // records in the global table as for DeskewBatchKernel, per-frame times (t_start, t_end, t_req) in a table of three
 // doubles, per-frame flags (bit 0 stamp out of range, bit 1 some w != 1).  72 B/point.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+template <int BLOCK, int MIN_CTAS>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS)
     DeskewCloudF64BatchKernel(const double* __restrict__ cloud, const double* __restrict__ stamps, double* __restrict__ out,
                               const int64_t* __restrict__ offsets, const kmc_b200_frame_params* __restrict__ table,
                               const double* __restrict__ times, int n_frames, int64_t n, int64_t item_points, double frames_per_point,
@@ -1060,10 +1060,21 @@ cudaError_t LaunchDeskewCloudF64Batch(const double* cloud, const double* stamps,
   int64_t const n_items = (n_points + item_points - 1) / item_points;
   unsigned const grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_items, static_cast<int64_t>(sm_count) * ctas)));
   double const fpp = static_cast<double>(n_frames) / static_cast<double>(n_points);
-  if (block == 128)
-    DeskewCloudF64BatchKernel<128><<<grid, 128, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, n_points, item_points, fpp, flags_dev);
-  else
-    DeskewCloudF64BatchKernel<256><<<grid, 256, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, n_points, item_points, fpp, flags_dev);
+  // registers: the nine column streams and the 16-float record want ~80 registers (3 CTAs of 256 per SM); capping them at 64 / 51
+  // trades a few local-memory reloads of loop invariants for residency (f64_min_ctas = 1 / 4 / 5; sweep in profiles/r02_sweep_f64_batch.log)
+  int const min_ctas = kmc_b200::internal::TuneValue("f64_min_ctas", 4);
+#define KMC_F64B(B, M) \
+  DeskewCloudF64BatchKernel<B, M><<<grid, B, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, n_points, item_points, fpp, flags_dev)
+  if (block == 128) {
+    if (min_ctas >= 10) KMC_F64B(128, 10);
+    else if (min_ctas >= 8) KMC_F64B(128, 8);
+    else KMC_F64B(128, 1);
+  } else {
+    if (min_ctas >= 5) KMC_F64B(256, 5);
+    else if (min_ctas >= 4) KMC_F64B(256, 4);
+    else KMC_F64B(256, 1);
+  }
+#undef KMC_F64B
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

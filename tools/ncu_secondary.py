@@ -3,8 +3,8 @@
 time stamps) on 20 M points, meant to run under `ncu --set full` so that their DRAM traffic per point can be put beside
 their algorithmic bytes:
 
-  ncu --set full --clock-control none -k regex:'Project|F64|DeskewFrame|PseudoTime' -o gpurun_out/secondary python tools/ncu_secondary.py
-  python tools/ncu_secondary.py --summarize gpurun_out/secondary.ncu-rep profiles/r01_ncu_secondary_kernels.csv
+  ncu --set full --clock-control none -k regex:'Project|F64|DeskewFrame|PseudoTime|Checksums|CheckFractions' -o gpurun_out/secondary python tools/ncu_secondary.py
+  python tools/ncu_secondary.py --summarize gpurun_out/secondary.ncu-rep profiles/r02_ncu_secondary_kernels.csv
 """
 import csv
 import io
@@ -19,7 +19,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 N = 20_000_000
 # kernel-name substring, template flags that tell the variants apart, algorithmic bytes per point
 ALGORITHMIC = [
-    ("DeskewFrameKernel", 32), ("PseudoTimeStampsKernel", 24), ("DeskewCloudF64Kernel", 72),
+    ("DeskewFrameKernel", 32), ("PseudoTimeStampsXyKernel", 24), ("PseudoTimeStampsKernel", 24), ("DeskewCloudF64BatchKernel", 72),
+    ("DeskewCloudF64Kernel", 72), ("FrameChecksumsKernel", 16), ("CheckFractionsKernel", 16),
+    ("DeskewProjectBatchKernel<0, 1, 1", 48), ("DeskewProjectBatchKernel<0, 4, 0", 80), ("DeskewProjectBatchKernel<0, 4, 1", 96),
     ("ProjectFrameKernel<0, 0", 32), ("ProjectFrameKernel<1, 1", 48), ("ProjectFrameKernel<1, 0", 32),
     ("ProjectFrame4Kernel<0, 0", 80), ("ProjectFrame4Kernel<1, 1", 96),
 ]
@@ -68,6 +70,27 @@ def launch_all():
     st = torch.empty(N, dtype=torch.float64, device="cuda")
     lib.kmc_b200_pseudo_time_stamps_device(C.c_void_p(d_in.data_ptr()), C.c_void_p(st.data_ptr()), C.c_int64(N), C.c_double(0.0),
                                            C.c_double(0.1), C.c_void_p(s))
+    # GetPseudoTimeStamps on the reference's double columns
+    lib.kmc_b200_pseudo_time_stamps_xy_device(C.c_void_p(cloud[0].data_ptr()), C.c_void_p(cloud[1].data_ptr()), C.c_void_p(st.data_ptr()),
+                                              C.c_int64(N), C.c_double(0.0), C.c_double(0.1), C.c_void_p(s))
+    # batch forms: 160 frames of 125 000 points = N
+    F, per = 160, N // 160
+    offs = torch.arange(0, (F + 1) * per, per, dtype=torch.int64, device="cuda")
+    bparams, _ = capi.synth_frame_params(F, 20110926, 0, 0.5)
+    d_par = torch.from_numpy(bparams.view(np.uint8).copy()).cuda()
+    times = torch.tensor([[0.0, 0.1, 0.05]] * F, dtype=torch.float64, device="cuda").reshape(-1)
+    bflags = torch.zeros(F, dtype=torch.int32, device="cuda")
+    flat = cloud.reshape(-1)
+    for f in range(F):  # frame f's w column inside its own 4 x per block
+        flat[4 * f * per + 3 * per:4 * (f + 1) * per] = 1.0
+    capi.deskew_cloud_f64_batch_device(flat.data_ptr(), stamps.data_ptr(), out64.data_ptr(), offs.data_ptr(), d_par.data_ptr(), times.data_ptr(), F, N,
+                                       bflags.data_ptr(), s)
+    capi.deskew_project_batch_device(d_in.data_ptr(), d_out.data_ptr(), pp[:1], offs.data_ptr(), d_par.data_ptr(), F, N, [cam], 0, s)
+    capi.deskew_project_batch_device(d_in.data_ptr(), 0, pp, offs.data_ptr(), d_par.data_ptr(), F, N, [cam] * 4, 0, s)
+    capi.deskew_project_batch_device(d_in.data_ptr(), d_out.data_ptr(), pp, offs.data_ptr(), d_par.data_ptr(), F, N, [cam] * 4, 0, s)
+    sums = torch.zeros(F, dtype=torch.int64, device="cuda")
+    capi.frame_checksums_device(d_out.data_ptr(), offs.data_ptr(), F, N, sums.data_ptr(), s)
+    capi.check_fractions_device(d_in.data_ptr(), N, bflags.data_ptr(), s)
     torch.cuda.synchronize()
 
 

@@ -434,51 +434,47 @@ __global__ void __launch_bounds__(kBlockThreads)
 // N_f x 4 matrix: x | y | z | w columns), the N_f stamps at stamps + offsets[f], and the same block of `out`.  Per-frame
 // records in the global table as for DeskewBatchKernel, per-frame times (t_start, t_end, t_req) in a table of three
 // doubles, per-frame flags (bit 0 stamp out of range, bit 1 some w != 1).  72 B/point.
-template <int BLOCK, int MIN_CTAS>
-__global__ void __launch_bounds__(BLOCK, MIN_CTAS)
+// Grid: blockIdx.y (+ z) is the FRAME, blockIdx.x one of gridDim.x CTAs that stride over the frame's tiles together — inside
+// a frame this is exactly DeskewCloudF64Kernel's access pattern (neighbouring CTAs read neighbouring 2 KB pieces of each of
+// the nine column streams at the same time, which is what keeps DRAM rows open), no frame search, and the hardware
+// scheduler hands out (frame, lane) pairs in frame order.  The first version cut the flat point range into 4096-point items
+// as DeskewBatchKernel does; with nine streams per item that gave 4.3-5.5 TB/s against 6.6 for the single-frame kernel
+// (profiles/r02_sweep_f64_batch.log).  The frame's 64-byte record sits in shared memory: in registers it costs 16 of them on top of
+// nine 64-bit column pointers (79 registers, 3 CTAs per SM).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
     DeskewCloudF64BatchKernel(const double* __restrict__ cloud, const double* __restrict__ stamps, double* __restrict__ out,
                               const int64_t* __restrict__ offsets, const kmc_b200_frame_params* __restrict__ table,
-                              const double* __restrict__ times, int n_frames, int64_t n, int64_t item_points, double frames_per_point,
-                              int* __restrict__ flags) {
-  int64_t const n_items = (n + item_points - 1) / item_points;
-  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-    int64_t p0 = item * item_points;
-    int64_t const p1 = (p0 + item_points < n) ? (p0 + item_points) : n;
-    int f = LocateFrame(offsets, n_frames, p0, frames_per_point);
-    while (p0 < p1 && f < n_frames) {
-      int64_t const frame_begin = __ldg(offsets + f);
-      int64_t const frame_end = __ldg(offsets + f + 1);
-      if (frame_end <= p0) {  // empty frame
-        ++f;
-        continue;
-      }
-      int64_t const seg_end = frame_end < p1 ? frame_end : p1;
-      kmc_b200_frame_params const P = LoadParamsWarpBroadcast(table, f);
-      double const t1 = __ldg(times + 3 * f), t2 = __ldg(times + 3 * f + 1), t_req = __ldg(times + 3 * f + 2);
-      double const duration = t2 - t1;
-      double const x_req = (t_req - t1) / duration;
-      int64_t const nf = frame_end - frame_begin;
-      const double* const c = cloud + 4 * frame_begin;
-      double* const o = out + 4 * frame_begin;
-      const double* const ts = stamps + frame_begin;
-      int bad = 0;
-      for (int64_t i = p0 - frame_begin + threadIdx.x; i < seg_end - frame_begin; i += BLOCK) {
-        double const x = __ldg(c + i), y = __ldg(c + nf + i), z = __ldg(c + 2 * nf + i), w = __ldg(c + 3 * nf + i);
-        double const t = __ldg(ts + i);
-        if (!(t >= t1 && t <= t2)) bad |= 1;
-        if (w != 1.0) bad |= 2;
-        float const s = static_cast<float>((t - t1) / duration - x_req);
-        float3 const d = DeskewDeltaW(static_cast<float>(x), static_cast<float>(y), static_cast<float>(z), static_cast<float>(w), s, P);
-        o[i] = x + static_cast<double>(d.x);
-        o[nf + i] = y + static_cast<double>(d.y);
-        o[2 * nf + i] = z + static_cast<double>(d.z);
-        o[3 * nf + i] = w;
-      }
-      if (bad) atomicOr(flags + f, bad);
-      p0 = seg_end;
-      ++f;
-    }
+                              const double* __restrict__ times, int n_frames, int* __restrict__ flags) {
+  __shared__ kmc_b200_frame_params record;
+  int const f = static_cast<int>(blockIdx.y) + static_cast<int>(blockIdx.z) * static_cast<int>(gridDim.y);
+  if (f >= n_frames) return;
+  int64_t const frame_begin = __ldg(offsets + f);
+  int64_t const nf = __ldg(offsets + f + 1) - frame_begin;
+  if (static_cast<int64_t>(blockIdx.x) * BLOCK >= nf) return;  // more CTAs per frame than this frame has tiles
+  if (threadIdx.x < 16) reinterpret_cast<float*>(&record)[threadIdx.x] = __ldg(reinterpret_cast<const float*>(table + f) + threadIdx.x);
+  double const t1 = __ldg(times + 3 * f), t2 = __ldg(times + 3 * f + 1), t_req = __ldg(times + 3 * f + 2);
+  __syncthreads();
+  double const duration = t2 - t1;
+  double const x_req = (t_req - t1) / duration;
+  const double* const c = cloud + 4 * frame_begin;
+  double* const o = out + 4 * frame_begin;
+  const double* const ts = stamps + frame_begin;
+  int64_t const stride = static_cast<int64_t>(gridDim.x) * BLOCK;
+  int bad = 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * BLOCK + threadIdx.x; i < nf; i += stride) {
+    double const x = __ldg(c + i), y = __ldg(c + nf + i), z = __ldg(c + 2 * nf + i), w = __ldg(c + 3 * nf + i);
+    double const t = __ldg(ts + i);
+    if (!(t >= t1 && t <= t2)) bad |= 1;
+    if (w != 1.0) bad |= 2;
+    float const s = static_cast<float>((t - t1) / duration - x_req);
+    float3 const d = DeskewDeltaW(static_cast<float>(x), static_cast<float>(y), static_cast<float>(z), static_cast<float>(w), s, record);
+    o[i] = x + static_cast<double>(d.x);
+    o[nf + i] = y + static_cast<double>(d.y);
+    o[2 * nf + i] = z + static_cast<double>(d.z);
+    o[3 * nf + i] = w;
   }
+  if (bad) atomicOr(flags + f, bad);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1054,27 +1050,16 @@ cudaError_t LaunchDeskewCloudF64Batch(const double* cloud, const double* stamps,
   if (n_frames <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(flags_dev, 0, static_cast<size_t>(n_frames) * sizeof(int), stream);
   if (e != cudaSuccess || n_points <= 0) return e;
+  // gridDim.x CTAs share a frame: enough of them that each strides over ~f64_item_tiles tiles of an average frame
   int const block = kmc_b200::internal::TuneValue("f64_block", 256) == 128 ? 128 : 256;
-  int const ctas = std::max(kmc_b200::internal::TuneValue("f64_ctas", 6), 1);
-  int64_t const item_points = static_cast<int64_t>(block) * std::max(1, kmc_b200::internal::TuneValue("f64_item_tiles", 16));
-  int64_t const n_items = (n_points + item_points - 1) / item_points;
-  unsigned const grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_items, static_cast<int64_t>(sm_count) * ctas)));
-  double const fpp = static_cast<double>(n_frames) / static_cast<double>(n_points);
-  // registers: the nine column streams and the 16-float record want ~80 registers (3 CTAs of 256 per SM); capping them at 64 / 51
-  // trades a few local-memory reloads of loop invariants for residency (f64_min_ctas = 1 / 4 / 5; sweep in profiles/r02_sweep_f64_batch.log)
-  int const min_ctas = kmc_b200::internal::TuneValue("f64_min_ctas", 4);
-#define KMC_F64B(B, M) \
-  DeskewCloudF64BatchKernel<B, M><<<grid, B, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, n_points, item_points, fpp, flags_dev)
-  if (block == 128) {
-    if (min_ctas >= 10) KMC_F64B(128, 10);
-    else if (min_ctas >= 8) KMC_F64B(128, 8);
-    else KMC_F64B(128, 1);
-  } else {
-    if (min_ctas >= 5) KMC_F64B(256, 5);
-    else if (min_ctas >= 4) KMC_F64B(256, 4);
-    else KMC_F64B(256, 1);
-  }
-#undef KMC_F64B
+  int64_t const tiles = std::max(1, kmc_b200::internal::TuneValue("f64_item_tiles", 16));
+  int64_t const avg = (n_points + n_frames - 1) / n_frames;
+  unsigned const gx = static_cast<unsigned>(std::min<int64_t>(std::max<int64_t>((avg + block * tiles - 1) / (block * tiles), 1), 65535));
+  unsigned const gy = static_cast<unsigned>(std::min<int32_t>(n_frames, 32768));
+  unsigned const gz = static_cast<unsigned>((n_frames + static_cast<int32_t>(gy) - 1) / static_cast<int32_t>(gy));
+  dim3 const grid(gx, gy, gz);
+  if (block == 128) DeskewCloudF64BatchKernel<128><<<grid, 128, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, flags_dev);
+  else DeskewCloudF64BatchKernel<256><<<grid, 256, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, flags_dev);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

@@ -74,10 +74,8 @@ def main():
     sweep("DeskewCloudF64BatchKernel 300 x 130 000", 72, nb,
           lambda: capi.deskew_cloud_f64_batch_device(cloud.data_ptr(), stamps.data_ptr(), out.data_ptr(), offs.data_ptr(), d_par.data_ptr(),
                                                      times.data_ptr(), F, nb, flags.data_ptr(), st),
-          f64_tunes + ["f64_ctas=4096,f64_item_tiles=4", "f64_ctas=4096,f64_item_tiles=64", "f64_ctas=4096,f64_block=128,f64_item_tiles=32",
-                       "f64_min_ctas=1", "f64_min_ctas=4", "f64_min_ctas=5", "f64_min_ctas=5,f64_ctas=5", "f64_min_ctas=4,f64_ctas=4",
-                       "f64_block=128,f64_min_ctas=8,f64_ctas=8", "f64_block=128,f64_min_ctas=10,f64_ctas=10", "f64_min_ctas=5,f64_ctas=4096",
-                       "f64_min_ctas=4,f64_ctas=4096", "f64_min_ctas=4,f64_ctas=4096,f64_item_tiles=8", "f64_min_ctas=5,f64_ctas=4096,f64_item_tiles=8"])
+          ["", "f64_item_tiles=4", "f64_item_tiles=8", "f64_item_tiles=32", "f64_item_tiles=64", "f64_block=128", "f64_block=128,f64_item_tiles=8",
+           "f64_block=128,f64_item_tiles=32", "f64_block=128,f64_item_tiles=64"])
     # ---- stamps
     xy_n = 100_000_000
     del cloud, out

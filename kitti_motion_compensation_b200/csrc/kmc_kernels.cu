@@ -1120,8 +1120,8 @@ cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* s
 cudaError_t LaunchCheckFractions(const float* xyzi, int64_t n, int* flags_dev, int sm_count, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(flags_dev, 0, sizeof(int), stream);
   if (e != cudaSuccess || n <= 0) return e;
-  int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
-  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  int64_t grid = (n + 4 * kBlockThreads - 1) / (4 * kBlockThreads);  // four points per thread, one CTA per 1024 points
+  int64_t const cap = static_cast<int64_t>(sm_count) * 4096;
   if (grid > cap) grid = cap;
   CheckFractionsKernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(reinterpret_cast<const float4*>(xyzi), n, flags_dev);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1133,8 +1133,8 @@ cudaError_t LaunchFrameChecksums(const float* xyzi, const int64_t* offsets_dev, 
   if (n_frames <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(sums_dev, 0, static_cast<size_t>(n_frames) * sizeof(uint64_t), stream);
   if (e != cudaSuccess || n_points <= 0) return e;
-  int64_t grid = (n_points + kChecksumItemPoints - 1) / kChecksumItemPoints;
-  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  int64_t grid = (n_points + kChecksumItemPoints - 1) / kChecksumItemPoints;  // one CTA per item (see PickConfig)
+  int64_t const cap = static_cast<int64_t>(sm_count) * 4096;
   if (grid > cap) grid = cap;
   FrameChecksumsKernel<<<static_cast<unsigned>(grid), kChecksumBlockThreads, 0, stream>>>(
       reinterpret_cast<const uint4*>(xyzi), offsets_dev, n_frames, n_points, static_cast<double>(n_frames) / static_cast<double>(n_points),

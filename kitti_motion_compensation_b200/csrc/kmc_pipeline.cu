@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -169,7 +170,22 @@ class SharedPool {
   template <class F>
   static void Run(int64_t n_blocks, F&& fn) {
     SharedPool& self = Instance();
-    std::lock_guard<std::mutex> lock(self.turn_);
+    // a turn lasts tens of microseconds (one pass over one chunk): spin for it before sleeping on the mutex — a futex
+    // sleep / wake pair costs about as much as the turn itself, and four concurrent MotionCompensateFrame callers ran at
+    // half the single caller's rate with a plain lock (profiles/r02_dropin_concurrent_callers_shared_pool.log)
+    std::unique_lock<std::mutex> lock(self.turn_, std::try_to_lock);
+    if (!lock.owns_lock()) {
+      auto const give_up = std::chrono::steady_clock::now() + std::chrono::microseconds(300);
+      for (int spins = 1; !lock.try_lock(); ++spins) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 63) == 0 && std::chrono::steady_clock::now() > give_up) {
+          lock.lock();
+          break;
+        }
+      }
+    }
     self.pool_.Run(n_blocks, std::forward<F>(fn));
   }
 

@@ -1092,11 +1092,12 @@ cudaError_t LaunchDeskewCloudF64(const double* cloud, const double* stamps, doub
 }
 
 cudaError_t LaunchDeskewDeltaColumns(const float* columns_in, float* columns_out, int64_t stride_points, bool has_w,
-                                     const kmc_b200_frame_params& params, int sm_count, cudaStream_t stream) {
+                                     const kmc_b200_frame_params& params, int sm_count, cudaStream_t stream, bool over_pcie) {
   if (stride_points <= 0) return cudaSuccess;
   int64_t const stride4 = stride_points / 4;
   int64_t grid = (stride4 + kDeltaBlockThreads - 1) / kDeltaBlockThreads;
-  int64_t const cap = static_cast<int64_t>(sm_count) * 8;
+  // columns in pinned host memory: a small grid keeps the number of PCIe read requests in flight low (profiles/r02_latency_probe.log)
+  int64_t const cap = static_cast<int64_t>(sm_count) * (over_pcie ? std::max(1, kmc_b200::internal::TuneValue("f64_zc_ctas", 2)) : 8);
   if (grid > cap) grid = cap;
   auto const* in4 = reinterpret_cast<const float4*>(columns_in);
   auto* out4 = reinterpret_cast<float4*>(columns_out);

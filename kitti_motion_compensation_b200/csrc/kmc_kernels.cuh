@@ -75,8 +75,9 @@ cudaError_t LaunchDeskewCloudF64Batch(const double* cloud, const double* stamps,
 
 // Narrow transport of the reference-layout host path: float columns x | y | z | s [| w] of stride_points entries each
 // (a multiple of 4, 16-byte aligned) -> float columns dx | dy | dz.
+// over_pcie: the columns are pinned HOST memory (zero copy); the grid is then kept small.
 cudaError_t LaunchDeskewDeltaColumns(const float* columns_in, float* columns_out, int64_t stride_points, bool has_w,
-                                     const kmc_b200_frame_params& params, int sm_count, cudaStream_t stream);
+                                     const kmc_b200_frame_params& params, int sm_count, cudaStream_t stream, bool over_pcie);
 
 cudaError_t LaunchPseudoTimeStampsXy(const double* x, const double* y, double* stamps, int64_t n, double start, double end,
                                      int sm_count, cudaStream_t stream);

@@ -624,6 +624,9 @@ int F64HostPipeline(kmc_b200_handle* h, F64Frame* frames, int32_t n_frames) {
     return KMC_B200_OK;
   };
 
+  int64_t total = 0;
+  for (int32_t f = 0; f < n_frames; ++f) total += frames[f].n;
+  bool const zero_copy = total <= TuneValue("f64_zc_points", 1000000);
   int64_t k = 0;  // chunk counter across all frames
   for (int32_t f = 0; f < n_frames; ++f) {
     F64Frame& fr = frames[f];
@@ -677,10 +680,16 @@ int F64HostPipeline(kmc_b200_handle* h, F64Frame* frames, int32_t n_frames) {
         });
       }
       cudaStream_t const st = h->stream[slot];
-      KMC_CUDA_TRY(cudaMemcpyAsync(d_up, up, static_cast<size_t>(has_w ? 5 : 4) * stride * sizeof(float), cudaMemcpyHostToDevice, st));
-      KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewDeltaColumns(d_up, d_down, stride, has_w, fr.P, h->sm_count, st));
-      KMC_CUDA_TRY(cudaMemcpyAsync(up + 5 * static_cast<size_t>(h->f64_chunk), d_down, static_cast<size_t>(3) * stride * sizeof(float),
-                                   cudaMemcpyDeviceToHost, st));
+      float* const down = up + 5 * static_cast<size_t>(h->f64_chunk);
+      if (zero_copy) {
+        // KITTI-size frames: the kernel reads the pinned columns and writes the pinned displacement columns itself — two
+        // copy-engine operations of ~1 MB cost more in fixed latency than SM-issued PCIe accesses lose (see StreamChunksImpl)
+        KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewDeltaColumns(up, down, stride, has_w, fr.P, h->sm_count, st, /*over_pcie=*/true));
+      } else {
+        KMC_CUDA_TRY(cudaMemcpyAsync(d_up, up, static_cast<size_t>(has_w ? 5 : 4) * stride * sizeof(float), cudaMemcpyHostToDevice, st));
+        KMC_CUDA_TRY(kmc_b200::dev::LaunchDeskewDeltaColumns(d_up, d_down, stride, has_w, fr.P, h->sm_count, st, false));
+        KMC_CUDA_TRY(cudaMemcpyAsync(down, d_down, static_cast<size_t>(3) * stride * sizeof(float), cudaMemcpyDeviceToHost, st));
+      }
       KMC_CUDA_TRY(cudaEventRecord(h->done[slot], st));
       pending[slot] = {f, first, count, true};
     }

@@ -253,3 +253,17 @@ def test_log_of_a_slightly_non_orthonormal_pose():
             u, _, vt = np.linalg.svd(T[:3, :3])
             R = u @ np.diag([1, 1, np.sign(np.linalg.det(u @ vt))]) @ vt
             assert np.abs(xi_ref[3:] - ob.so3_log(R)).max() < 1e-10
+
+
+def test_eigen_provider_is_recorded_and_can_be_required():
+    """oracle/_ref is the reference's statements + whatever supplies Eigen: real Eigen 3 when the build box has it, this
+    repository's eigen_shim.hpp otherwise (this image: no Eigen on disk, no network).  The provider is recorded with the
+    library, reported by bench.py in its cpu_baseline sample, and a CI that does have Eigen can demand it:
+    KMC_REQUIRE_EIGEN3=1 turns the shim into a failure instead of a silent pass."""
+    import os
+    provider = rb.eigen_provider()
+    assert provider in ("eigen3", "shim")
+    recorded = os.path.join(os.path.dirname(rb.__file__), "_ref", "EIGEN_PROVIDER")
+    assert open(recorded).read().strip() == provider
+    if os.environ.get("KMC_REQUIRE_EIGEN3") == "1":
+        assert provider == "eigen3", "oracle/_ref was built against the Eigen shim; install Eigen 3 and run `make -C oracle ref`"

@@ -14,7 +14,7 @@ NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --
 CXXFLAGS  := -std=c++17 -O2 -fPIC -Wall -Wextra
 
 KERNEL_SRC := $(CSRC)/kmc_kernels.cu $(CSRC)/kmc_kernels_bulk.cu $(CSRC)/kmc_capi.cu $(CSRC)/kmc_pipeline.cu $(CSRC)/kmc_host_math.cpp $(CSRC)/kmc_run.cpp
-KERNEL_HDR := $(CSRC)/kmc_kernels.cuh $(CSRC)/kmc_point_math.cuh $(CSRC)/kmc_host_math.hpp $(CSRC)/kmc_internal.hpp $(INC)/kmc_b200.h
+KERNEL_HDR := $(CSRC)/kmc_kernels.cuh $(CSRC)/kmc_point_math.cuh $(CSRC)/kmc_host_math.hpp $(CSRC)/kmc_internal.hpp $(CSRC)/kmc_host_pool.hpp $(INC)/kmc_b200.h
 MIRROR_HDR := $(wildcard $(INC)/kitti_motion_compensation/*.hpp)
 
 all: $(LIB)/libkmc_b200.so $(LIB)/libkitti_motion_compensation_lib.so
@@ -26,7 +26,9 @@ $(LIB)/libkmc_b200.so: $(KERNEL_SRC) $(KERNEL_HDR)
 $(LIB)/libkitti_motion_compensation_lib.so: $(CSRC)/kmc_dropin.cpp $(MIRROR_HDR) $(INC)/kmc_b200.h $(LIB)/libkmc_b200.so
 	$(CXX) $(CXXFLAGS) -shared -I $(INC) -o $@ $< -L $(LIB) -lkmc_b200 '-Wl,-rpath,$$ORIGIN'
 
-example: $(LIB)/motion_compensate_runs
+example: $(LIB)/motion_compensate_runs $(LIB)/bench_motion_compensate_frame
+$(LIB)/bench_motion_compensate_frame: examples/bench_motion_compensate_frame.cpp $(LIB)/libkitti_motion_compensation_lib.so
+	$(CXX) -std=c++17 -O2 -Wall -I $(INC) -o $@ $< -L $(LIB) -lkitti_motion_compensation_lib -lkmc_b200 -lpthread '-Wl,-rpath,$$ORIGIN'
 $(LIB)/motion_compensate_runs: examples/motion_compensate_runs.cpp $(LIB)/libkitti_motion_compensation_lib.so
 	$(CXX) -std=c++17 -O2 -Wall -I $(INC) -o $@ $< -L $(LIB) -lkitti_motion_compensation_lib -lkmc_b200 '-Wl,-rpath,$$ORIGIN'
 
@@ -37,7 +39,7 @@ oracle:
 cpp-tests: all
 	@mkdir -p tests/cpp/_build
 	for t in test_dropin_host test_dropin_gpu; do \
-	  $(CXX) -std=c++17 -O1 -Wall -I $(INC) -I tests/cpp -o tests/cpp/_build/$$t tests/cpp/$$t.cpp -L $(LIB) -lkitti_motion_compensation_lib -lkmc_b200 -Wl,-rpath,$(abspath $(LIB)); done
+	  $(CXX) -std=c++17 -O1 -Wall -I $(INC) -I tests/cpp -o tests/cpp/_build/$$t tests/cpp/$$t.cpp -L $(LIB) -lkitti_motion_compensation_lib -lkmc_b200 -lpthread -Wl,-rpath,$(abspath $(LIB)); done
 	$(CXX) -std=c++17 -O1 -Wall -Wextra -pedantic -Werror -I $(INC) -I tests/cpp -o tests/cpp/_build/test_eigen_shim tests/cpp/test_eigen_shim.cpp
 
 clean:

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libkmc_b200.so")
 DROPIN_LIB_PATH = os.path.join(LIB_DIR, "libkitti_motion_compensation_lib.so")
 
 SOURCES = ["kmc_kernels.cu", "kmc_kernels_bulk.cu", "kmc_capi.cu", "kmc_pipeline.cu", "kmc_host_math.cpp", "kmc_run.cpp"]
-HEADERS = ["kmc_kernels.cuh", "kmc_point_math.cuh", "kmc_host_math.hpp", "kmc_internal.hpp", os.path.join(REPO_DIR, "include", "kmc_b200.h")]
+HEADERS = ["kmc_kernels.cuh", "kmc_point_math.cuh", "kmc_host_math.hpp", "kmc_internal.hpp", "kmc_host_pool.hpp", os.path.join(REPO_DIR, "include", "kmc_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -105,7 +105,7 @@ def build_cpp_test(name: str, force: bool = False) -> str:
     if not force and not _stale(out, [src, os.path.join(tests, "mini_gtest.hpp"), DROPIN_LIB_PATH]):
         return out
     cmd = [_cxx(), "-std=c++17", "-O1", "-Wall", "-I", os.path.join(REPO_DIR, "include"), "-I", tests, "-o", out, src,
-           "-L", LIB_DIR, "-lkitti_motion_compensation_lib", "-lkmc_b200", f"-Wl,-rpath,{LIB_DIR}"]
+           "-L", LIB_DIR, "-lkitti_motion_compensation_lib", "-lkmc_b200", "-lpthread", f"-Wl,-rpath,{LIB_DIR}"]
     subprocess.run(cmd, check=True)
     return out
 

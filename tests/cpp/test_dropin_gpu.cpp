@@ -10,6 +10,8 @@
 #include <iterator>
 #include <memory>
 #include <random>
+#include <thread>
+#include <vector>
 
 #include "kitti_motion_compensation/camera_model.hpp"
 #include "kitti_motion_compensation/data_handle.hpp"
@@ -166,6 +168,49 @@ TEST(RealScanTest, LoadAndMotionCompensate) {
   }
   double const ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count() / reps;
   std::printf("    kmc::MotionCompensateFrame(Frame, t): %.3f ms per 123 397-point frame = %.1f Mpoints/s\n", ms, 123397.0 / ms / 1e3);
+}
+
+// The reference's MotionCompensateFrame touches only its arguments, i.e. it is re-entrant; here concurrent callers lease
+// separate handles and share the host thread pool.  Six threads, different requested times and a non-homogeneous column in
+// one of them: every result equals the same call made alone.
+TEST(RealScanTest, ConcurrentCallersGetTheSingleCallerResult) {
+  KittiPclLoader loader;
+  auto [cloud, intensities] = loader.LoadPointcloud(g_real_scan);
+  Time const start{47072.283701593}, middle{47072.335337762}, end{47072.386973931};
+  VectorXd const stamps{GetPseudoTimeStamps(cloud, start, end)};
+  Oxts const oxts{47072.349659964, 49.011212804408, 8.4228850417969, 112.83492279053, 0.022447, 1e-05, -1.2219096732051, 0, 0, 0};
+  Affine3d const T_start{OxtsToPose(oxts)};
+  Twist xi;
+  xi << 1.34, 0.03, -0.01, -0.003, 0.004, 0.05;
+  Affine3d const T_end{T_start * lie::Exp(xi)};
+  constexpr int kCallers = 6;
+  std::vector<Frame> frames;
+  std::vector<Time> requested;
+  for (int c = 0; c < kCallers; ++c) {
+    Pointcloud mine = cloud;
+    if (c == 3) mine(1234, 3) = 2.0;  // w != 1 in one caller's cloud: R p + t w for that point
+    frames.emplace_back(T_start, T_end, LidarScan{start, middle, end, mine, intensities, stamps});
+    requested.push_back(start + (end - start) * static_cast<double>(c) / (kCallers - 1));
+  }
+  std::vector<Pointcloud> alone;
+  for (int c = 0; c < kCallers; ++c) alone.push_back(MotionCompensateFrame(frames[static_cast<size_t>(c)], requested[static_cast<size_t>(c)]));
+  std::vector<int> mismatches(kCallers, 0);
+  std::vector<std::thread> callers;
+  for (int c = 0; c < kCallers; ++c) {
+    callers.emplace_back([&, c] {
+      for (int rep = 0; rep < 10; ++rep) {
+        Pointcloud const out{MotionCompensateFrame(frames[static_cast<size_t>(c)], requested[static_cast<size_t>(c)])};
+        Pointcloud const& want = alone[static_cast<size_t>(c)];
+        for (Index i = 0; i < out.rows(); ++i)
+          for (int k = 0; k < 4; ++k)
+            if (out(i, k) != want(i, k)) ++mismatches[static_cast<size_t>(c)];
+      }
+    });
+  }
+  for (auto& t : callers) t.join();
+  for (int c = 0; c < kCallers; ++c) ASSERT_EQ(mismatches[static_cast<size_t>(c)], 0);
+  ASSERT_TRUE(alone[3](1234, 3) == 2.0);
+  ASSERT_TRUE(alone[0](0, 0) != alone[5](0, 0));  // different requested times do give different clouds
 }
 
 // test/test_data_io.cpp:115-149 — write -> read round trip of the float32 xyzi format

@@ -67,9 +67,10 @@ def main():
 
     log(f"host threads on this box: {os.cpu_count()}")
     log("== kmc::MotionCompensateFrame(Frame const&, Time), real 123 397-point scan, one caller ==")
-    for tune in ["", "f64_zc_points=0", "f64_zc_ctas=1", "f64_zc_ctas=4", "f64_zc_ctas=8", "f64_parts=1", "f64_parts=3", "f64_parts=4",
-                 "f64_parts=1,f64_zc_points=0", "f64_parts=4,f64_zc_points=0", "host_threads=1", "host_threads=2", "host_threads=4",
-                 "host_threads=6", "host_threads=12", "host_threads=16", "f64_parts=4,f64_zc_ctas=1", "f64_parts=3,f64_zc_ctas=4"]:
+    for tune in ["", "f64_zc_points=0", "f64_chunk=131072,f64_parts=1", "f64_chunk=131072,f64_parts=1,f64_zc_ctas=8", "f64_chunk=131072,f64_parts=1,f64_zc_ctas=4",
+                 "f64_chunk=131072,f64_parts=1,f64_zc_ctas=8,host_threads=12", "f64_chunk=131072,f64_parts=2,f64_zc_ctas=8", "f64_zc_ctas=8,host_threads=12",
+                 "f64_chunk=131072,f64_parts=1,f64_zc_ctas=16", "f64_chunk=131072,f64_parts=1,f64_zc_points=0", "", "f64_chunk=131072,f64_parts=1,f64_zc_ctas=8",
+                 "host_threads=1", "host_threads=2", "host_threads=4", "host_threads=12"]:
         log(f"{tune or 'default':34s} {json.dumps(dropin(tune))}")
     log("== the same, 2 / 4 / 8 concurrent callers (handle leases) ==")
     for threads in (2, 4, 8):

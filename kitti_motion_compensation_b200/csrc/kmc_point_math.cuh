@@ -41,24 +41,10 @@ __device__ __forceinline__ float Atan2Turns(float y, float x) {
   return copysignf(q, y);
 }
 
-// The same in double, for the GetPseudoTimeStamps entry points (timestamp_mocking.cpp:46-63), whose stamps are doubles of
-// magnitude ~4.7e4 s: libdevice's atan2 costs ~120 FP64 instructions per point and made those kernels FP64-bound
-// (3.5 TB/s); this costs ~30.  atan(r)/(2 pi r) on [0,1] as a degree-12 interpolant in r^2 at Chebyshev nodes:
-// |err| < 1e-12 turns evaluated in double, i.e. < 1e-13 s on a 0.1 s scan (1 ulp of the stamps is 7e-12 s).
-// The quotient min/max comes from the fp32 reciprocal refined by one Newton step in double (relative error ~1e-14).
-__device__ __forceinline__ double Atan2TurnsF64(double y, double x) {
-  double const ax = fabs(x), ay = fabs(y);
-  double const mx = fmax(ax, ay), mn = fmin(ax, ay);
-  double r;
-  if (mx > 1e-30 && mx < 1e30) {
-    float seed;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(static_cast<float>(mx)));
-    double const x0 = static_cast<double>(seed);
-    r = mn * (x0 * fma(-mx, x0, 2.0));
-  } else {
-    r = (mx > 0.0) ? mn / mx : 0.0;  // atan2(+-0, +-0): no 0/0; values outside the fp32 range take the exact quotient
-  }
-  double const t = r * r;
+// atan(r)/(2 pi r) on [0,1] as a degree-12 interpolant in t = r^2 at Chebyshev nodes: |err| < 1e-12 turns evaluated in double,
+// i.e. < 1e-13 s on a 0.1 s scan (1 ulp of KITTI's stamps, ~4.7e4 s, is 7e-12 s).  libdevice's double atan2 costs ~120 FP64
+// instructions per point and made the stamp kernels FP64-bound (3.5 TB/s).
+__device__ __forceinline__ double AtanOverTwoPiR(double t) {
   double p = 6.67221862187784099e-05;
   p = fma(p, t, -5.08567722343806756e-04);
   p = fma(p, t, 1.81876432393576174e-03);
@@ -72,16 +58,47 @@ __device__ __forceinline__ double Atan2TurnsF64(double y, double x) {
   p = fma(p, t, 3.18309541393976964e-02);
   p = fma(p, t, -5.30516470898420370e-02);
   p = fma(p, t, 1.59154943090102946e-01);
-  double q = r * p;
-  q = (ay > ax) ? (0.25 - q) : q;
-  q = (__double2hiint(x) < 0) ? (0.5 - q) : q;  // sign BIT of x
-  q = (x != x || y != y) ? __longlong_as_double(0x7ff8000000000000ll) : q;  // fmax / fmin drop a NaN operand, atan2 does not
-  return copysign(q, y);
+  return p;
+}
+
+// FractionOfScanCompleted (timestamp_mocking.cpp:46) = (pi - atan2(y, x)) / 2 pi for DOUBLE coordinates (the reference's
+// column-major cloud), for the GetPseudoTimeStamps entry points (timestamp_mocking.cpp:56-63).
+// Only the quotient min/max (fp32 reciprocal + one Newton step in double, relative error ~1e-14), the polynomial and the final
+// fold run in FP64.  The octant logic runs in fp32 on the rounded magnitudes: sign bits are exact, and which of |x|, |y| is the
+// larger only matters away from the diagonal — where the two agree to float precision both folds evaluate to the same
+// 1e-12 (the interpolant holds slightly beyond r = 1).  The folds collapse into frac = A + B q with small exact constants, which
+// keeps the axis points exact: 1 for y = -0, x < 0; 0 for y = +0, x < 0; 0.5 for x = y = 0.  Magnitudes outside the fp32 range
+// (and NaNs) take an exact slow path.  ~70 instructions per point instead of ~100 with the logic in FP64.
+__device__ __forceinline__ double FractionOfScanXYF64(double y, double x) {
+  double const ax = fabs(x), ay = fabs(y);
+  float const fax = static_cast<float>(ax), fay = static_cast<float>(ay);
+  bool steep = fay > fax;
+  float const fmx = steep ? fay : fax;
+  double r;
+  if (fmx > 1e-30f && fmx < 1e30f) {
+    double const mx = steep ? ay : ax, mn = steep ? ax : ay;
+    float seed;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(fmx));
+    double const x0 = static_cast<double>(seed);
+    r = mn * (x0 * fma(-mx, x0, 2.0));
+  } else {  // zero, denormal-in-float, huge, infinite or NaN magnitudes: exact comparison and quotient
+    steep = ay > ax;
+    double const mx = steep ? ay : ax, mn = steep ? ax : ay;
+    r = (mx > 0.0) ? ((mn == mx) ? 1.0 : mn / mx) : 0.0;  // atan2(+-0, +-0): no 0/0; inf/inf counts as the diagonal
+  }
+  double const q = r * AtanOverTwoPiR(r * r);  // atan(min/max) / 2 pi in [0, 1/8]
+  // turns = sy (c + m q);  frac = 0.5 - turns = (0.5 - sy c) + (-sy m) q
+  bool const back = __double2hiint(x) < 0;  // sign BIT of x: atan2(+-0, -0) = +-pi
+  float const c = steep ? 0.25f : (back ? 0.5f : 0.0f);
+  float const m = (steep != back) ? -1.0f : 1.0f;
+  float const sy = (__double2hiint(y) < 0) ? -1.0f : 1.0f;
+  float const a = (fax != fax || fay != fay) ? __int_as_float(0x7fc00000) : 0.5f - sy * c;  // atan2 of a NaN is NaN
+  return fma(static_cast<double>(-sy * m), q, static_cast<double>(a));
 }
 
 // FractionOfScanCompleted (timestamp_mocking.cpp:46) in double for a point whose coordinates ARE floats (the .bin
 // layout): the octant logic — |x| vs |y|, the sign bits — is exact in fp32, so only the quotient, the polynomial and the
-// final fold run in double.  The two folds of Atan2TurnsF64 collapse into frac = A + B q with A, B small exact constants
+// final fold run in double.  The two folds collapse into frac = A + B q with A, B small exact constants
 // picked in fp32, which keeps q = 0 (a point on an axis) exact: frac = 1 for y = -0, x < 0; 0 for y = +0, x < 0; 0.5 for
 // x = y = 0.  ~45 instructions per point instead of ~150.  Domain: |x|, |y| < 1e30 (larger values give r = 0).
 __device__ __forceinline__ double FractionOfScanF64(float y, float x) {
@@ -93,21 +110,7 @@ __device__ __forceinline__ double FractionOfScanF64(float y, float x) {
   double const x0 = static_cast<double>(seed);
   double const dmx = static_cast<double>(mx);
   double const r = static_cast<double>(mn) * (x0 * fma(-dmx, x0, 2.0));  // one Newton step: relative error ~1e-14
-  double const t = r * r;
-  double p = 6.67221862187784099e-05;
-  p = fma(p, t, -5.08567722343806756e-04);
-  p = fma(p, t, 1.81876432393576174e-03);
-  p = fma(p, t, -4.13898280986435812e-03);
-  p = fma(p, t, 6.94657045892680715e-03);
-  p = fma(p, t, -9.58462323410399705e-03);
-  p = fma(p, t, 1.19290805724528125e-02);
-  p = fma(p, t, -1.44022158368946745e-02);
-  p = fma(p, t, 1.76746446101705770e-02);
-  p = fma(p, t, -2.27356426872162426e-02);
-  p = fma(p, t, 3.18309541393976964e-02);
-  p = fma(p, t, -5.30516470898420370e-02);
-  p = fma(p, t, 1.59154943090102946e-01);
-  double const q = r * p;  // atan(min/max) / 2 pi in [0, 1/8]
+  double const q = r * AtanOverTwoPiR(r * r);  // atan(min/max) / 2 pi in [0, 1/8]
   // turns = sy (c + m q);  frac = 0.5 - turns = (0.5 - sy c) + (-sy m) q
   bool const steep = ay > ax, back = (__float_as_uint(x) >> 31) != 0;
   float const c = steep ? 0.25f : (back ? 0.5f : 0.0f);

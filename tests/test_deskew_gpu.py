@@ -450,6 +450,43 @@ def test_pseudo_time_stamps_device(capi, oracle, cuda):
     assert got[0] == t0 + 1.0 * (t2 - t0) and got[1] == t0  # frac exactly 1 and 0
 
 
+def test_pseudo_time_stamps_on_double_columns(capi, oracle, cuda):
+    """kmc_b200_pseudo_time_stamps_xy_host — what kmc::GetPseudoTimeStamps(Pointcloud const&, Time, Time) calls: x and y are the
+    first two columns of the reference's column-major DOUBLE cloud (timestamp_mocking.cpp:56-63).  The kernel's octant logic runs
+    in fp32 on the rounded magnitudes, so the cases that could expose it are here: coordinates that are not float-representable,
+    points within float resolution of the diagonals in all four quadrants, magnitudes outside the fp32 range, signed zeros,
+    infinities and NaNs."""
+    rng = np.random.default_rng(11)
+    real = helpers.real_scan()[:, :2].astype(np.float64) + rng.uniform(-1e-9, 1e-9, (123_397, 2))
+    eps = np.array([0.0, 1e-16, -1e-16, 1e-12, -1e-12, 1e-9, -1e-9, 3e-8, -3e-8, 6e-8, -6e-8, 1e-7, -1e-7, 1e-6, -1e-6, 1e-3, -1e-3])
+    base = rng.uniform(0.5, 100.0, len(eps))
+    diag = np.concatenate([np.stack([sx * base, sy * base * (1.0 + eps)], axis=1) for sx in (1, -1) for sy in (1, -1)])
+    scale = np.concatenate([real[:200] * 1e-200, real[:200] * 1e200, real[:200] * 1e-35, real[:200] * 1e35, real[:200] * 1e-42,
+                            np.stack([real[:200, 0] * 1e-40, real[:200, 1] * 1e40], axis=1), np.stack([real[:200, 0] * 1e300, real[:200, 1] * 1e250], axis=1)])
+    z, nz, inf = 0.0, -0.0, np.inf
+    special = np.array([[1, z], [1, nz], [-1, z], [-1, nz], [z, 1], [nz, 1], [z, -1], [nz, -1], [z, z], [nz, z], [z, nz], [nz, nz],
+                        [inf, 1], [-inf, 1], [-inf, -1], [1, inf], [1, -inf], [inf, inf], [-inf, inf], [-inf, -inf], [inf, -inf]], dtype=np.float64)
+    xy = np.concatenate([special, diag, scale, real])
+    cloud = np.concatenate([xy, np.zeros((len(xy), 1)), np.ones((len(xy), 1))], axis=1)
+    with capi.Handle(0, 1024) as h:
+        with np.errstate(all="ignore"):
+            frac = h.pseudo_time_stamps(xy[:, 0], xy[:, 1], 0.0, 1.0)          # unit scan from 0: the stamp IS the fraction
+            want = (np.pi - np.arctan2(xy[:, 1], xy[:, 0])) / (2 * np.pi)      # timestamp_mocking.cpp:46 in numpy's libm
+        assert np.abs(frac - want).max() < 2e-12, int(np.abs(frac - want).argmax())
+        assert frac[:12].tolist() == [0.5, 0.5, 0.0, 1.0, 0.25, 0.25, 0.75, 0.75, 0.5, 0.0, 0.5, 1.0]  # axis points exact
+        assert frac[12:17].tolist() == [0.5, 0.0, 1.0, 0.25, 0.75]                                     # one infinite coordinate: an axis
+        t0, t2 = 47072.283701593, 47072.386973931
+        got = h.pseudo_time_stamps(xy[:, 0], xy[:, 1], t0, t2)
+        ref = oracle.pseudo_time_stamps(cloud, t0, t2)
+        assert np.abs(got - ref).max() < 2.5e-11  # 1 ulp of a ~4.7e4 s stamp is 7.3e-12 s
+        bad = xy[:6].copy()
+        bad[1, 0] = np.nan
+        bad[4, 1] = np.nan
+        st = h.pseudo_time_stamps(bad[:, 0], bad[:, 1], t0, t2)
+        assert np.isnan(st[[1, 4]]).all() and np.array_equal(st[[0, 2, 3, 5]], got[[0, 2, 3, 5]])
+        assert h.pseudo_time_stamps(np.zeros(0), np.zeros(0), t0, t2).size == 0
+
+
 # ---- full-size properties (BASELINE configs 3 and 5), no oracle needed ---------------------------------------------------
 def test_synthetic_generator_is_seeded_and_shard_independent(capi, cuda):
     torch = cuda

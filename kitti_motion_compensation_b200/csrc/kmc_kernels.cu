@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(kBlockThreads)
                              double start, double duration) {
   int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; i < n; i += stride) {
-    stamps[i] = fma(FractionOfScanXYF64(__ldg(y + i), __ldg(x + i)), duration, start);
+    stamps[i] = fma(0.5 - Atan2TurnsF64(__ldg(y + i), __ldg(x + i)), duration, start);
   }
 }
 

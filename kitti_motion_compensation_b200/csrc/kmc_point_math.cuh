@@ -61,39 +61,29 @@ __device__ __forceinline__ double AtanOverTwoPiR(double t) {
   return p;
 }
 
-// FractionOfScanCompleted (timestamp_mocking.cpp:46) = (pi - atan2(y, x)) / 2 pi for DOUBLE coordinates (the reference's
-// column-major cloud), for the GetPseudoTimeStamps entry points (timestamp_mocking.cpp:56-63).
-// Only the quotient min/max (fp32 reciprocal + one Newton step in double, relative error ~1e-14), the polynomial and the final
-// fold run in FP64.  The octant logic runs in fp32 on the rounded magnitudes: sign bits are exact, and which of |x|, |y| is the
-// larger only matters away from the diagonal — where the two agree to float precision both folds evaluate to the same
-// 1e-12 (the interpolant holds slightly beyond r = 1).  The folds collapse into frac = A + B q with small exact constants, which
-// keeps the axis points exact: 1 for y = -0, x < 0; 0 for y = +0, x < 0; 0.5 for x = y = 0.  Magnitudes outside the fp32 range
-// (and NaNs) take an exact slow path.  ~70 instructions per point instead of ~100 with the logic in FP64.
-__device__ __forceinline__ double FractionOfScanXYF64(double y, double x) {
+// atan2(y, x) / (2 pi) in turns for DOUBLE coordinates (the reference's column-major cloud), for the GetPseudoTimeStamps entry
+// points (timestamp_mocking.cpp:56-63).  The quotient min/max comes from the fp32 reciprocal refined by one Newton step in
+// double (relative error ~1e-14); magnitudes outside the fp32 range take the exact quotient.  A variant with the octant logic
+// in fp32 (as FractionOfScanF64 below) was measured and is SLOWER here — 3.57 vs 5.39 TB/s: the extra f32 <-> f64 conversions
+// cost more than the FP64 compares they replace (profiles/r02_sweep_secondary.log vs the run after it).
+__device__ __forceinline__ double Atan2TurnsF64(double y, double x) {
   double const ax = fabs(x), ay = fabs(y);
-  float const fax = static_cast<float>(ax), fay = static_cast<float>(ay);
-  bool steep = fay > fax;
-  float const fmx = steep ? fay : fax;
+  double const mx = fmax(ax, ay), mn = fmin(ax, ay);
   double r;
-  if (fmx > 1e-30f && fmx < 1e30f) {
-    double const mx = steep ? ay : ax, mn = steep ? ax : ay;
+  if (mx > 1e-30 && mx < 1e30) {
     float seed;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(fmx));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(static_cast<float>(mx)));
     double const x0 = static_cast<double>(seed);
     r = mn * (x0 * fma(-mx, x0, 2.0));
-  } else {  // zero, denormal-in-float, huge, infinite or NaN magnitudes: exact comparison and quotient
-    steep = ay > ax;
-    double const mx = steep ? ay : ax, mn = steep ? ax : ay;
-    r = (mx > 0.0) ? ((mn == mx) ? 1.0 : mn / mx) : 0.0;  // atan2(+-0, +-0): no 0/0; inf/inf counts as the diagonal
+  } else {
+    // atan2(+-0, +-0): no 0/0; inf/inf counts as the diagonal; values outside the fp32 range take the exact quotient
+    r = (mx > 0.0) ? ((mn == mx) ? 1.0 : mn / mx) : 0.0;
   }
-  double const q = r * AtanOverTwoPiR(r * r);  // atan(min/max) / 2 pi in [0, 1/8]
-  // turns = sy (c + m q);  frac = 0.5 - turns = (0.5 - sy c) + (-sy m) q
-  bool const back = __double2hiint(x) < 0;  // sign BIT of x: atan2(+-0, -0) = +-pi
-  float const c = steep ? 0.25f : (back ? 0.5f : 0.0f);
-  float const m = (steep != back) ? -1.0f : 1.0f;
-  float const sy = (__double2hiint(y) < 0) ? -1.0f : 1.0f;
-  float const a = (fax != fax || fay != fay) ? __int_as_float(0x7fc00000) : 0.5f - sy * c;  // atan2 of a NaN is NaN
-  return fma(static_cast<double>(-sy * m), q, static_cast<double>(a));
+  double q = r * AtanOverTwoPiR(r * r);
+  q = (ay > ax) ? (0.25 - q) : q;
+  q = (__double2hiint(x) < 0) ? (0.5 - q) : q;  // sign BIT of x
+  q = (x != x || y != y) ? __longlong_as_double(0x7ff8000000000000ll) : q;  // fmax / fmin drop a NaN operand, atan2 does not
+  return copysign(q, y);
 }
 
 // FractionOfScanCompleted (timestamp_mocking.cpp:46) in double for a point whose coordinates ARE floats (the .bin

@@ -319,6 +319,19 @@ def run_reference(args):
     return 0
 
 
+def shards_bit_equal(gathered, whole, n_frames, world, shard_range):
+    """The cross-GPU bit-equality check of the strong-scaling leg: gathered[r] holds rank r's per-frame checksums of ITS shard
+    (padded to a common length for all_gather), `whole` the checksums of the single-GPU result over the whole batch; shard r
+    owns frames shard_range(n_frames, world, r).  Returns (all equal, frames compared)."""
+    import torch
+    equal, compared = True, 0
+    for r in range(world):
+        b, e = shard_range(n_frames, world, r)
+        equal = equal and bool(torch.equal(gathered[r][: e - b], whole[b:e]))
+        compared += e - b
+    return equal, compared
+
+
 def copy_ceiling(torch, device, pin_in, pin_out, barrier, reps=6):
     """Plain concurrent H2D + D2H of the e2e step's bytes (one cudaMemcpyAsync each way per rep on two streams): what the
     box gives any host-buffer path when every rank uses its link at the same time.  Returns seconds for `reps` reps."""
@@ -537,11 +550,7 @@ def run_b200(args):
         dist.all_gather(gathered, mine)
         strong_value = args.scans * points * args.steps / (s_elapsed_max * 1e-3) / 1e6
         if rank == 0:
-            equal, compared = True, 0
-            for r in range(world):
-                rb_, re_ = capi.shard_range(args.scans, world, r)
-                equal = equal and bool(torch.equal(gathered[r][: re_ - rb_], sums_g1[rb_:re_]))
-                compared += re_ - rb_
+            equal, compared = shards_bit_equal(gathered, sums_g1, args.scans, world, capi.shard_range)
             nonzero = bool((sums_g1 != 0).all().item())
             one_gpu_ms = elapsed_ms_max / args.steps  # one GPU over the whole batch (the weak leg's step, max over ranks)
             strong = {"value": round(strong_value, 1), "unit": UNIT, "ms_per_step": round(s_elapsed_max / args.steps, 4),

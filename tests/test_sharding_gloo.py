@@ -57,6 +57,56 @@ def test_two_rank_sharding_and_reduction(tmp_path):
     assert parts.tobytes() == whole.view(np.uint8).tobytes()
 
 
+def _checksum_worker(rank, world, port, n_frames, corrupt_rank, out_dir):
+    """What bench.py's strong-scaling leg does after its timed region, with numpy standing in for the GPU: every rank
+    checksums the frames of ITS shard, the checksums are all-gathered (padded to a common length), rank 0 compares them with
+    the checksums of the whole batch computed in one piece."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    from kitti_motion_compensation_b200 import capi
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    points = 257
+
+    def frame(f):  # the "deskewed output" of frame f: depends on the frame only, never on the rank that produced it
+        return np.random.default_rng(1000 + f).standard_normal((points, 4)).astype(np.float32)
+
+    b, e = capi.shard_range(n_frames, world, rank)
+    shard = np.concatenate([frame(f) for f in range(b, e)]) if e > b else np.zeros((0, 4), np.float32)
+    if rank == corrupt_rank and e > b:
+        shard.view(np.uint32)[points * ((e - b) // 2) + 5, 1] ^= 1  # one flipped bit in one frame of this rank's shard
+    sums = capi.frame_checksums_numpy(shard, np.arange(0, (e - b + 1) * points, points))
+    cap = -(-n_frames // world)
+    mine = torch.zeros(cap, dtype=torch.int64)
+    mine[: e - b] = torch.from_numpy(sums.view(np.int64))
+    gathered = [torch.zeros(cap, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    if rank == 0:
+        whole = np.concatenate([frame(f) for f in range(n_frames)])
+        whole_sums = torch.from_numpy(capi.frame_checksums_numpy(whole, np.arange(0, (n_frames + 1) * points, points)).view(np.int64))
+        equal, compared = bench.shards_bit_equal(gathered, whole_sums, n_frames, world, capi.shard_range)
+        np.save(os.path.join(out_dir, f"equal_{corrupt_rank}.npy"), np.array([int(equal), compared]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_checksums_compare_like_the_strong_leg(tmp_path):
+    """bench.py's `shards_bit_equal` over a gloo all-gather: equal when every rank holds the right bits, false when one bit of
+    one frame on one rank differs (frame counts that do not divide evenly included)."""
+    sys.path.insert(0, ROOT)
+    from kitti_motion_compensation_b200 import build
+    build.build()
+    world, n_frames = 2, 11
+    for corrupt_rank in (-1, 1):
+        mp.spawn(_checksum_worker, args=(world, _free_port(), n_frames, corrupt_rank, str(tmp_path)), nprocs=world, join=True)
+        equal, compared = np.load(tmp_path / f"equal_{corrupt_rank}.npy")
+        assert compared == n_frames
+        assert bool(equal) == (corrupt_rank < 0)
+
+
 def test_bench_reference_arm_runs_on_cpu_and_prints_one_json_line():
     """bench.py --impl reference (the oracle port on the host cores) must work without a GPU and under torchrun env."""
     import json

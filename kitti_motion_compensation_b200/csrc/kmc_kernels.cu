@@ -19,8 +19,9 @@
 // golden test), or from half-angle polynomials valid to pi when a scan rotates by more than 1 rad.
 //
 // Memory: the N x 4 float32 "x y z i" array is read once and written once (32 B/point), 128-bit or 256-bit
-// (sm_100 LDG.256/STG.256) accesses, fully coalesced, several independent loads in flight per thread, persistent grid
-// sized in multiples of the SM count.  HBM-bandwidth bound; no shared memory, no tensor cores (nothing to contract).
+// (sm_100 LDG.256/STG.256) accesses, fully coalesced, one CTA of 128 threads per work item — the hardware scheduler balances
+// SMs of different speed better than a persistent grid does (PickConfig).  HBM-bandwidth bound; no shared memory, no tensor
+// cores (nothing to contract).
 #include "kmc_internal.hpp"
 #include "kmc_kernels.cuh"
 #include "kmc_point_math.cuh"

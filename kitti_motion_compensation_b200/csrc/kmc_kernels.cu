@@ -1047,7 +1047,7 @@ cudaError_t LaunchDeskewProjectBatch(const float* in, float* cloud_out, float* c
 
 cudaError_t LaunchDeskewCloudF64Batch(const double* cloud, const double* stamps, double* out, const int64_t* offsets_dev,
                                       const kmc_b200_frame_params* params_dev, const double* times_dev, int32_t n_frames, int64_t n_points,
-                                      int* flags_dev, int sm_count, cudaStream_t stream) {
+                                      int* flags_dev, int /*sm_count: the grid is (lanes per frame) x (frames)*/, cudaStream_t stream) {
   if (n_frames <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(flags_dev, 0, static_cast<size_t>(n_frames) * sizeof(int), stream);
   if (e != cudaSuccess || n_points <= 0) return e;

@@ -436,7 +436,7 @@ int kmc_b200_handle_set_file_callback(kmc_b200_handle* h, kmc_b200_file_done_fn 
 }
 
 int kmc_b200_handle_device(const kmc_b200_handle* h) { return h ? h->device : KMC_B200_ERR_NULL_POINTER; }
-int64_t kmc_b200_handle_capacity(const kmc_b200_handle* h) { return h ? h->capacity : KMC_B200_ERR_NULL_POINTER; }
+int64_t kmc_b200_handle_capacity(const kmc_b200_handle* h) { return h ? h->capacity : static_cast<int64_t>(KMC_B200_ERR_NULL_POINTER); }
 
 // ---- host entry points -------------------------------------------------------------------------------------------------
 int kmc_b200_deskew_frame_host(kmc_b200_handle* h, const float* in, float* out, int64_t n, const kmc_b200_frame_params* params,

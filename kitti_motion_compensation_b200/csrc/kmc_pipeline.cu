@@ -241,8 +241,9 @@ int64_t NextChunkPoints(int64_t chunk_index, int64_t remaining, int64_t capacity
   return std::max<int64_t>(c & ~int64_t{1023}, 1024);  // ramp sizes only: whole multiples of 1024 points
 }
 
-// Chunks of a zero-copy transfer: one launch for pinned caller memory; with pageable memory the staging copies of one piece
-// overlap the kernel of the other, so the transfer is cut in `zc_parts` pieces (default 2).
+// Chunks of a zero-copy transfer: one launch per slot-sized piece (`zc_parts` = 1).  Cutting a scan into 2-3 pieces so that the
+// staging copies of pageable memory overlap the neighbouring piece's kernel did not pay (131 vs 136-147 us per 130 000-point scan,
+// profiles/r02_sweep_single_scan.log): every extra launch + event costs what the overlap wins.
 int64_t ZeroCopyChunkPoints(int64_t remaining, int64_t capacity, int64_t total) {
   int64_t const parts = std::max(1, TuneValue("zc_parts", 1));
   int64_t const c = std::max<int64_t>(8192, ((total + parts - 1) / parts + 1023) & ~int64_t{1023});

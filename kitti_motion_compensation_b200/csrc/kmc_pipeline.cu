@@ -160,7 +160,7 @@ int StreamChunks(kmc_b200_handle* h, int64_t n, bool zero_copy, Fetch&& fetch, L
   return rc;
 }
 
-// The library's host threads: ONE pool per process, min(8, hardware threads / 2) - 1 workers beside the calling thread
+// The library's host threads: ONE pool per process, min(12, 3/4 of the hardware threads) - 1 workers beside the calling thread
 // (KMC_B200_TUNE host_threads=N), created on first use and never torn down.  Handles share it and take turns: the host
 // passes of concurrent callers run one after the other at full width while their copies and kernels overlap on the
 // devices — a pool per handle oversubscribes the cores as soon as a few threads call at once (8 callers x 8 threads on a
@@ -196,7 +196,7 @@ class SharedPool {
   }
   static int Workers() {
     unsigned const hw = std::max(1u, std::thread::hardware_concurrency());
-    int const dflt = static_cast<int>(std::min(8u, std::max(2u, hw / 2)));
+    int const dflt = static_cast<int>(std::min(12u, std::max(2u, 3 * hw / 4)));  // 1 / 2 / 4 / 8 / 12 threads: 570 / 328 / 169 / 137 / 128 us per KITTI frame
     return std::min(std::max(TuneValue("host_threads", dflt) - 1, 0), 63);
   }
   SharedPool() : pool_(Workers()) {}

@@ -72,9 +72,6 @@ struct kmc_b200_handle {
   int64_t* d_offsets = nullptr;
   kmc_b200_frame_params* d_params = nullptr;
   int64_t table_capacity = 0;  // frames
-  // scratch of the double-precision (reference layout) entry points, grown on demand and kept
-  double* d_f64 = nullptr;
-  size_t d_f64_bytes = 0;
   // narrow-transport staging of kmc_b200_deskew_cloud_f64_host: per slot 5 float columns up and 3 down, pinned + device
   float* f64_pinned = nullptr;
   float* f64_device = nullptr;
@@ -100,21 +97,9 @@ void FreeHandle(kmc_b200_handle* h) {
   }
   if (h->d_offsets) cudaFree(h->d_offsets);
   if (h->d_params) cudaFree(h->d_params);
-  if (h->d_f64) cudaFree(h->d_f64);
   if (h->f64_pinned) cudaFreeHost(h->f64_pinned);
   if (h->f64_device) cudaFree(h->f64_device);
   delete h;
-}
-
-int EnsureF64Scratch(kmc_b200_handle* h, size_t bytes) {
-  if (bytes <= h->d_f64_bytes) return KMC_B200_OK;
-  if (h->d_f64) cudaFree(h->d_f64);
-  h->d_f64 = nullptr;
-  h->d_f64_bytes = 0;
-  size_t const want = bytes + bytes / 4;  // head room: clouds of a run differ by a few percent in size
-  KMC_CUDA_TRY(cudaMalloc(&h->d_f64, want));
-  h->d_f64_bytes = want;
-  return KMC_B200_OK;
 }
 
 int EnsureTables(kmc_b200_handle* h, int64_t n_frames) {
@@ -769,6 +754,10 @@ int kmc_b200_deskew_cloud_f64_batch_host(kmc_b200_handle* h, const double* const
 }
 KMC_CATCH_AT_BOUNDARY("deskew_cloud_f64_batch_host")
 
+// GetPseudoTimeStamps (timestamp_mocking.cpp:56-63) for HOST columns.  Round 1 issued three cudaMemcpyAsync on pageable Eigen
+// memory (the driver stages those through its own bounce buffers at ~10 GB/s).  Now the columns are staged into the slot's
+// pinned buffer by the host pool, and for KITTI-size clouds the kernel reads them — and writes the stamps — in pinned memory
+// directly (zero copy, see StreamChunksImpl); large clouds go through the copy engines in slot-sized chunks over three slots.
 int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, const double* y, int64_t n, double start, double end,
                                         double* stamps) try {
   TraceRange const trace("kmc_b200_pseudo_time_stamps_xy_host");
@@ -779,17 +768,58 @@ int kmc_b200_pseudo_time_stamps_xy_host(kmc_b200_handle* h, const double* x, con
   std::lock_guard<std::mutex> lock(h->mu);
   DeviceGuard const guard(h->device);
   KMC_CUDA_TRY(guard.status());
-  size_t const bytes = static_cast<size_t>(n) * sizeof(double);
-  if (int rc = EnsureF64Scratch(h, 3 * bytes)) return rc;
-  double* d = h->d_f64;  // x | y | stamps
-  cudaStream_t const st = h->stream[0];
-  cudaError_t e = cudaMemcpyAsync(d, x, bytes, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, y, bytes, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = kmc_b200::dev::LaunchPseudoTimeStampsXy(d, d + n, d + 2 * n, n, start, end, h->sm_count, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(stamps, d + 2 * n, bytes, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return FailCuda(e, "pseudo_time_stamps_xy_host");
-  return KMC_B200_OK;
+  constexpr int kSlots = kmc_b200_handle::kSlots;
+  bool const zero_copy = n <= TuneValue("zc_points", 2000000);
+  // a slot holds capacity x 16 bytes: x | y of `capacity` points in h_in / d_in, their stamps in the first half of h_out / d_out
+  int64_t const parts = zero_copy ? std::max(1, TuneValue("stamp_parts", 2)) : 1;
+  int64_t const chunk = std::min(h->capacity, std::max<int64_t>(8192, ((n + parts - 1) / parts + 1023) & ~int64_t{1023}));
+  struct Pending {
+    int64_t first = 0, count = 0;
+    bool active = false;
+  } pending[kSlots];
+  auto retire = [&](int slot) -> int {
+    if (!pending[slot].active) return KMC_B200_OK;
+    KMC_CUDA_TRY(cudaEventSynchronize(h->done[slot]));
+    StagingCopy(h, stamps + pending[slot].first, h->h_out[slot], static_cast<size_t>(pending[slot].count) * sizeof(double));
+    pending[slot].active = false;
+    return KMC_B200_OK;
+  };
+  auto body = [&]() -> int {
+    int64_t k = 0;
+    for (int64_t first = 0; first < n; first += chunk, ++k) {
+      int const slot = static_cast<int>(k % kSlots);
+      if (int rc = retire(slot)) return rc;
+      int64_t const count = std::min(chunk, n - first);
+      size_t const col = static_cast<size_t>(count) * sizeof(double);
+      auto* const hx = reinterpret_cast<double*>(h->h_in[slot]);
+      auto* const hs = reinterpret_cast<double*>(h->h_out[slot]);
+      StagingCopy(h, hx, x + first, col);
+      StagingCopy(h, hx + count, y + first, col);
+      cudaStream_t const st = h->stream[slot];
+      if (zero_copy) {
+        KMC_CUDA_TRY(kmc_b200::dev::LaunchPseudoTimeStampsXy(hx, hx + count, hs, count, start, end, h->sm_count, st));
+      } else {
+        auto* const dx = reinterpret_cast<double*>(h->d_in[slot]);
+        auto* const ds = reinterpret_cast<double*>(h->d_out[slot]);
+        KMC_CUDA_TRY(cudaMemcpyAsync(dx, hx, 2 * col, cudaMemcpyHostToDevice, st));
+        KMC_CUDA_TRY(kmc_b200::dev::LaunchPseudoTimeStampsXy(dx, dx + count, ds, count, start, end, h->sm_count, st));
+        KMC_CUDA_TRY(cudaMemcpyAsync(hs, ds, col, cudaMemcpyDeviceToHost, st));
+      }
+      KMC_CUDA_TRY(cudaEventRecord(h->done[slot], st));
+      pending[slot] = {first, count, true};
+    }
+    for (int j = 0; j < kSlots; ++j)
+      if (int rc = retire(static_cast<int>((k + j) % kSlots))) return rc;  // oldest first
+    return KMC_B200_OK;
+  };
+  int const rc = body();
+  if (rc != KMC_B200_OK) {
+    std::string const keep = LastError();
+    for (int s2 = 0; s2 < kSlots; ++s2) cudaStreamSynchronize(h->stream[s2]);
+    cudaGetLastError();
+    LastError() = keep;
+  }
+  return rc;
 }
 KMC_CATCH_AT_BOUNDARY("pseudo_time_stamps_xy_host")
 

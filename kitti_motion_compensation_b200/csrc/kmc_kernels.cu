@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kBlockThreads)
 // (profiles/r02_sweep_f64_batch.log).  The frame's 64-byte record sits in shared memory: in registers it costs 16 of them on top of
 // nine 64-bit column pointers (79 registers, 3 CTAs per SM).
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)  // 64 registers, no spills, 4 CTAs of 256 threads per SM
     DeskewCloudF64BatchKernel(const double* __restrict__ cloud, const double* __restrict__ stamps, double* __restrict__ out,
                               const int64_t* __restrict__ offsets, const kmc_b200_frame_params* __restrict__ table,
                               const double* __restrict__ times, int n_frames, int* __restrict__ flags) {

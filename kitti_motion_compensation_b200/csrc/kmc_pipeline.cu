@@ -333,12 +333,12 @@ kmc_b200::dev::LaunchConfig PickHostCallConfig(const kmc_b200_handle* h, int64_t
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
     cfg.bulk = 0;
-    cfg.hint = 0;
-    cfg.unroll = 1;
+    cfg.hint = TuneValue("zc_hint", 0) == 1 ? 1 : 0;
+    cfg.unroll = TuneValue("zc_unroll", 1) == 2 ? 2 : 1;
     cfg.block = TuneValue("zc_block", 256);
     cfg.ctas_per_sm = std::max(1, TuneValue("zc_ctas", 1));
     cfg.vec = (TuneValue("zc_vec", 1) == 2 && aligned32) ? 2 : 1;
-    cfg.item_tiles = std::max(1, TuneValue("zc_tiles", 1));
+    cfg.item_tiles = std::max(1, TuneValue("zc_tiles", 4));  // 70.9-71.3 us vs 72.5-73.3 with 1 tile; every other shape 71-86 (profiles/r02_sweep_single_scan_fine.log)
     if (cfg.block != 128 && cfg.block != 512) cfg.block = 256;
   } else {
     cudaGetLastError();

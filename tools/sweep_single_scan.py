@@ -57,8 +57,8 @@ def main():
         lines.append(s)
 
     log("== one 130 000-point scan, zero-copy shape sweep (us, median of 300) ==")
-    for tune in ["", "zc_points=0", "zc_ctas=2", "zc_block=128", "zc_block=128,zc_ctas=2", "zc_block=512", "zc_vec=2", "zc_vec=2,zc_block=128",
-                 "zc_tiles=2", "zc_tiles=4", "zc_parts=2", "zc_parts=3", "zc_vec=2,zc_parts=2", "zc_block=128,zc_ctas=1,zc_tiles=2"]:
+    for tune in ["", "zc_tiles=4", "zc_tiles=2", "zc_unroll=2", "zc_unroll=2,zc_tiles=2", "zc_hint=1", "zc_hint=1,zc_tiles=4", "zc_block=512", "zc_block=512,zc_tiles=2",
+                 "zc_block=128,zc_ctas=2,zc_tiles=4", "zc_ctas=2,zc_tiles=4", "", "zc_tiles=4", "zc_tiles=8", "zc_unroll=2,zc_tiles=4", "zc_points=0"]:
         log(f"{tune or 'default (zero copy, 1 x 256 per SM, 128-bit)':52s} {json.dumps(run(tune, [130_000]))}")
     log("== scan size: zero copy vs copy-engine pipeline (zc_points=0) ==")
     sizes = [32_768, 65_536, 130_000, 250_000, 500_000, 1_000_000, 2_000_000]

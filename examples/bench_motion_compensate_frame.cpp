@@ -49,6 +49,22 @@ int main(int argc, char** argv) {
   }
   std::sort(stamp_us.begin(), stamp_us.end());
 
+  // eight frames: a loop of MotionCompensateFrame calls against one kmc::MotionCompensateFrames call (one pipeline)
+  std::vector<const kmc::Frame*> const eight(8, &frame);
+  std::vector<kmc::Time> const eight_times(8, middle);
+  std::vector<double> loop_us, batch_us;
+  for (int r = 0; r < 30; ++r) {
+    auto const a = std::chrono::steady_clock::now();
+    for (int k = 0; k < 8; ++k) (void)kmc::MotionCompensateFrame(frame, middle);
+    auto const b = std::chrono::steady_clock::now();
+    (void)kmc::MotionCompensateFrames(eight, eight_times);
+    auto const c = std::chrono::steady_clock::now();
+    loop_us.push_back(std::chrono::duration<double, std::micro>(b - a).count() / 8);
+    batch_us.push_back(std::chrono::duration<double, std::micro>(c - b).count() / 8);
+  }
+  std::sort(loop_us.begin(), loop_us.end());
+  std::sort(batch_us.begin(), batch_us.end());
+
   std::vector<std::vector<double>> us(static_cast<size_t>(threads));
   double checksum{0.0};
   auto worker = [&](int id) {
@@ -75,8 +91,10 @@ int main(int argc, char** argv) {
   double const median{all[all.size() / 2]};
   std::printf("{\"api\": \"kmc::MotionCompensateFrame(Frame const&, Time)\", \"points\": %.0f, \"reps\": %d, \"threads\": %d, "
               "\"us_median\": %.2f, \"us_min\": %.2f, \"us_p90\": %.2f, \"mpoints_per_s_median_call\": %.2f, "
-              "\"mpoints_per_s_aggregate\": %.2f, \"checksum\": %.9f, \"get_pseudo_time_stamps_us_median\": %.2f}\n",
+              "\"mpoints_per_s_aggregate\": %.2f, \"checksum\": %.9f, \"get_pseudo_time_stamps_us_median\": %.2f, "
+              "\"eight_frames_loop_us_per_frame\": %.2f, \"eight_frames_batch_call_us_per_frame\": %.2f}\n",
               n, reps, threads, median, all.front(), all[all.size() * 9 / 10], n / median,
-              n * static_cast<double>(reps) * threads / wall_s / 1e6, checksum, stamp_us[stamp_us.size() / 2]);
+              n * static_cast<double>(reps) * threads / wall_s / 1e6, checksum, stamp_us[stamp_us.size() / 2], loop_us[loop_us.size() / 2],
+              batch_us[batch_us.size() / 2]);
   return 0;
 }

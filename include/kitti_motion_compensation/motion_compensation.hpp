@@ -10,6 +10,8 @@
 // the reference's double result to ~2e-7 m for KITTI-range clouds.
 #pragma once
 
+#include <vector>
+
 #include "kitti_motion_compensation/data_types.hpp"
 #include "kitti_motion_compensation/trajectory_interpolation.hpp"
 
@@ -27,5 +29,11 @@ Pointcloud MotionCompensateFrame(const Frame& frame, const Time t_requested);
 
 // Selects the CUDA device used by the calls above (default 0).  Addition of this implementation.
 void SetMotionCompensationDevice(int device_ordinal);
+
+// Several frames at once (addition of this implementation): what a caller that loops MotionCompensateFrame over the frames
+// of a run does (handlers.cpp:55-64, 67-92), as ONE pipeline — the host passes, transfers and kernels of neighbouring frames
+// overlap instead of draining at the end of every frame (kmc_b200_deskew_cloud_f64_batch_host).  result[k] is bit-identical
+// to MotionCompensateFrame(*frames[k], requested_times[k]); the same abort rules apply to every frame.
+std::vector<Pointcloud> MotionCompensateFrames(const std::vector<const Frame*>& frames, const std::vector<Time>& requested_times);
 
 }  // namespace kmc

@@ -302,6 +302,54 @@ KMC_EXPORT Pointcloud MotionCompensateFrame(Frame const& frame, Time const reque
   return result;
 }
 
+KMC_EXPORT std::vector<Pointcloud> MotionCompensateFrames(std::vector<const Frame*> const& frames, std::vector<Time> const& requested_times) {
+  if (frames.size() != requested_times.size()) throw std::invalid_argument("MotionCompensateFrames: frames and requested_times differ in length");
+  size_t const F{frames.size()};
+  std::vector<Pointcloud> results;
+  results.reserve(F);
+  std::vector<kmc_b200_frame_params> params(F);
+  std::vector<const double*> clouds(F), stamps(F);
+  std::vector<double*> outs(F);
+  std::vector<std::int64_t> n_points(F);
+  std::vector<double> times(3 * F);
+  for (size_t k{0}; k < F; ++k) {
+    if (!frames[k]) throw std::invalid_argument("MotionCompensateFrames: null frame");
+    Frame const& frame{*frames[k]};
+    Time const t1{frame.scan.stamp_start}, t2{frame.scan.stamp_end};
+    Index const n{frame.scan.cloud.rows()};
+    if (frame.scan.timestamps.size() != n) throw std::invalid_argument("MotionCompensateFrames: scan.timestamps and scan.cloud differ in length");
+    double p1[16], p2[16];
+    ToBuffer(frame.T_start, p1);
+    ToBuffer(frame.T_end, p2);
+    int const rc{kmc_b200_frame_params_from_poses(p1, p2, t1, t2, requested_times[k], &params[k])};
+    if (rc == KMC_B200_ERR_TIME_OUT_OF_RANGE || rc == KMC_B200_ERR_EMPTY_INTERVAL) {
+      if (n == 0 && rc == KMC_B200_ERR_TIME_OUT_OF_RANGE) {  // the reference's loop never runs for an empty cloud
+        params[k] = kmc_b200_frame_params{};
+        times[3 * k] = 0.0, times[3 * k + 1] = 1.0, times[3 * k + 2] = 0.5;
+      } else {
+        AbortOutOfRange("MotionCompensateFrames", requested_times[k], t1, t2);
+      }
+    } else {
+      ThrowUnlessOk(rc, "kmc_b200_frame_params_from_poses");
+      times[3 * k] = t1, times[3 * k + 1] = t2, times[3 * k + 2] = requested_times[k];
+    }
+    results.emplace_back(MatrixX4d(n, 4));
+    clouds[k] = frame.scan.cloud.data();
+    stamps[k] = frame.scan.timestamps.data();
+    outs[k] = results.back().data();
+    n_points[k] = n;
+  }
+  if (F == 0) return results;
+  std::vector<int> flags(F, 0);
+  HandleLease const lease;
+  int const rc{kmc_b200_deskew_cloud_f64_batch_host(lease.get(), clouds.data(), stamps.data(), outs.data(), n_points.data(), times.data(),
+                                                    params.data(), static_cast<std::int32_t>(F), flags.data())};
+  for (size_t k{0}; k < F; ++k)
+    if (flags[k] & 1) AbortOutOfRange("MotionCompensateFrames (a point stamp)", std::nan(""), times[3 * k], times[3 * k + 1]);
+  ThrowUnlessOk(rc, "kmc_b200_deskew_cloud_f64_batch_host");
+  return results;
+}
+
 // ---- utils ------------------------------------------------------------------------------------------------------------
 KMC_EXPORT std::string IdToZeroPaddedString(size_t const id, size_t const pad) {
   std::string digits{std::to_string(id)};

@@ -213,6 +213,47 @@ TEST(RealScanTest, ConcurrentCallersGetTheSingleCallerResult) {
   ASSERT_TRUE(alone[0](0, 0) != alone[5](0, 0));  // different requested times do give different clouds
 }
 
+// kmc::MotionCompensateFrames (addition): the loop of handlers.cpp:55-64 as one pipeline; bit-identical to the per-frame calls.
+TEST(RealScanTest, FramesBatchEqualsPerFrameCalls) {
+  KittiPclLoader loader;
+  auto [cloud, intensities] = loader.LoadPointcloud(g_real_scan);
+  Time const start{47072.283701593}, middle{47072.335337762}, end{47072.386973931};
+  VectorXd const stamps{GetPseudoTimeStamps(cloud, start, end)};
+  Oxts const oxts{47072.349659964, 49.011212804408, 8.4228850417969, 112.83492279053, 0.022447, 1e-05, -1.2219096732051, 0, 0, 0};
+  Affine3d const T_start{OxtsToPose(oxts)};
+  std::vector<Frame> frames;
+  std::vector<Time> requested;
+  for (int k = 0; k < 5; ++k) {
+    Twist xi;
+    xi << 1.0 + 0.2 * k, 0.03, -0.01, -0.003, 0.004, 0.05 - 0.02 * k;
+    Pointcloud mine = MatrixX4d(k == 2 ? 0 : cloud.rows() - 1000 * k, 4);  // different sizes, one empty frame
+    VectorXd my_stamps(mine.rows()), my_intensities(mine.rows());
+    for (Index i = 0; i < mine.rows(); ++i) {
+      mine.row(i) = Vector4d{cloud(i, 0), cloud(i, 1), cloud(i, 2), 1.0};
+      my_stamps(i) = stamps(i);
+      my_intensities(i) = intensities(i);
+    }
+    frames.emplace_back(T_start, T_start * lie::Exp(xi), LidarScan{start, middle, end, mine, my_intensities, my_stamps});
+    requested.push_back(k % 2 ? start : middle);
+  }
+  std::vector<const Frame*> pointers;
+  for (auto const& f : frames) pointers.push_back(&f);
+  std::vector<Pointcloud> const batch{MotionCompensateFrames(pointers, requested)};
+  ASSERT_EQ(batch.size(), frames.size());
+  for (size_t k = 0; k < frames.size(); ++k) {
+    Pointcloud const one{MotionCompensateFrame(frames[k], requested[k])};
+    ASSERT_EQ(batch[k].rows(), one.rows());
+    int mismatches{0};
+    for (Index i = 0; i < one.rows(); ++i)
+      for (int c = 0; c < 4; ++c)
+        if (batch[k](i, c) != one(i, c)) ++mismatches;
+    ASSERT_EQ(mismatches, 0);
+  }
+  ASSERT_EQ(batch[2].rows(), 0);
+  ASSERT_TRUE(MotionCompensateFrames({}, {}).empty());
+  EXPECT_DEATH(MotionCompensateFrames(pointers, std::vector<Time>(5, end + 1.0)), "c");
+}
+
 // test/test_data_io.cpp:115-149 — write -> read round trip of the float32 xyzi format
 TEST(DataIoTest, SavePointcloud) {
   fs::path const dir{fs::temp_directory_path() / "kmc_b200_test_io"};

@@ -4,6 +4,7 @@
 #   make oracle     oracle/libkmc_oracle.so (CPU restatement) and, where /root/reference exists, oracle/_ref/libkmc_ref.so (the
 #                   reference's own sources compiled unmodified) — test infrastructure only
 #   make cpp-tests  tests/cpp/_build/test_{dropin_host,dropin_gpu,eigen_shim}
+#   make ref-tests  the reference's own test/*.cpp, unmodified, against the drop-in (tests/cpp/_ref_build/build/)
 NVCC      ?= nvcc
 CXX       ?= g++
 PKG       := kitti_motion_compensation_b200
@@ -42,7 +43,16 @@ cpp-tests: all
 	  $(CXX) -std=c++17 -O1 -Wall -I $(INC) -I tests/cpp -o tests/cpp/_build/$$t tests/cpp/$$t.cpp -L $(LIB) -lkitti_motion_compensation_lib -lkmc_b200 -lpthread -Wl,-rpath,$(abspath $(LIB)); done
 	$(CXX) -std=c++17 -O1 -Wall -Wextra -pedantic -Werror -I $(INC) -I tests/cpp -o tests/cpp/_build/test_eigen_shim tests/cpp/test_eigen_shim.cpp
 
+# the reference's OWN gtest files, unmodified, against the drop-in (needs the reference checkout; binaries in tests/cpp/_ref_build/build,
+# run from there so that "../testing_assets" resolves; same as kitti_motion_compensation_b200.build.build_reference_tests())
+REF ?= /root/reference
+ref-tests: all
+	@mkdir -p tests/cpp/_ref_build/build
+	@[ -d tests/cpp/_ref_build/testing_assets ] || (mkdir -p tests/cpp/_ref_build && cp -r $(REF)/testing_assets tests/cpp/_ref_build/ && rm -rf tests/cpp/_ref_build/testing_assets/*/*/image_0*)
+	for t in test_motion_compensation test_timestamp_mocking test_lie_algebra test_trajectory_interpolation test_oxts_to_pose; do \
+	  $(CXX) -std=c++17 -O1 -I tests/cpp/gtest_stub -I $(INC) -o tests/cpp/_ref_build/build/$$t $(REF)/test/$$t.cpp -L $(LIB) -lkitti_motion_compensation_lib -lkmc_b200 -lpthread '-Wl,-rpath,$$ORIGIN/../../../../$(LIB)'; done
+
 clean:
 	rm -f $(LIB)/*.so $(LIB)/motion_compensate_runs; rm -rf tests/cpp/_build; $(MAKE) -C oracle clean
 
-.PHONY: all example oracle cpp-tests clean
+.PHONY: all example oracle cpp-tests ref-tests clean

@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 
 #include <fcntl.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -189,18 +192,50 @@ class SharedPool {
   std::mutex turn_;
 };
 
+// A copy whose destination will not be read by this core again (a staging slot the DMA engine reads next, or the caller's
+// result buffer): non-temporal stores skip the read-for-ownership of the destination lines, i.e. 2 instead of 3 bytes of
+// memory traffic per byte copied.  A long host stream through pageable buffers is bound by exactly that traffic (stage +
+// DMA + DMA + unstage); glibc's memcpy only switches to streaming stores far above the 256 KB blocks used here.
+void StreamingCopy(void* dst, const void* src, size_t bytes) {
+#if defined(__SSE2__)
+  auto* d = static_cast<char*>(dst);
+  auto const* s = static_cast<const char*>(src);
+  size_t const head = std::min(bytes, (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15);
+  if (head) std::memcpy(d, s, head);
+  size_t i = head;
+  for (; i + 64 <= bytes; i += 64) {
+    __m128i const a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+    __m128i const b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
+    __m128i const c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32));
+    __m128i const e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
+  }
+  _mm_sfence();
+  if (i < bytes) std::memcpy(d + i, s + i, bytes - i);
+#else
+  std::memcpy(dst, src, bytes);
+#endif
+}
+
 // Pageable caller memory is staged through the handle's pinned slots.  One thread copies about 10-15 GB/s, a quarter of
-// what the PCIe link moves, so copies of 512 KB and more are cut into 256 KB blocks for the handle's host threads.
+// what the PCIe link moves, so copies of 512 KB and more are cut into 256 KB blocks for the library's host threads; long
+// transfers (>= 8 MB, which no cache will hold until they are read again) use streaming stores.
 void StagingCopy(kmc_b200_handle*, void* dst, const void* src, size_t bytes) {
   constexpr size_t kBlock = size_t{256} << 10;
   if (bytes < 2 * kBlock) {
     std::memcpy(dst, src, bytes);
     return;
   }
+  bool const streaming = bytes >= (size_t{8} << 20) && TuneValue("nt_copy", 1) != 0;
   int64_t const blocks = static_cast<int64_t>((bytes + kBlock - 1) / kBlock);
   SharedPool::Run(blocks, [=](int64_t b) {
     size_t const begin = static_cast<size_t>(b) * kBlock;
-    std::memcpy(static_cast<char*>(dst) + begin, static_cast<const char*>(src) + begin, std::min(kBlock, bytes - begin));
+    size_t const len = std::min(kBlock, bytes - begin);
+    if (streaming) StreamingCopy(static_cast<char*>(dst) + begin, static_cast<const char*>(src) + begin, len);
+    else std::memcpy(static_cast<char*>(dst) + begin, static_cast<const char*>(src) + begin, len);
   });
 }
 

@@ -54,7 +54,11 @@ def main():
     # pageable caller memory (numpy arrays): staged through the handle's pinned slots on the host side
     page_in = pin_in.numpy().copy()
     page_out = np.empty_like(page_in)
-    for chunk_scans in (1, 8, 32):
+    for chunk_scans, tune in ((1, ""), (8, ""), (32, ""), (8, "nt_copy=0"), (32, "nt_copy=0"), (8, "host_threads=16"), (32, "host_threads=8")):
+        os.environ.pop("KMC_B200_TUNE", None)
+        if tune:
+            os.environ["KMC_B200_TUNE"] = tune
+            print(f"KMC_B200_TUNE={tune} (host_threads only takes effect in a fresh process)", flush=True)
         with capi.Handle(0, chunk_scans * points) as h:
             h.deskew_batch_ptr(page_in.ctypes.data, page_out.ctypes.data, offs, params)
             t0 = time.perf_counter()

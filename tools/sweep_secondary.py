@@ -84,7 +84,7 @@ def main():
     ts = torch.empty(xy_n, dtype=torch.float64, device="cuda")
     sweep("PseudoTimeStampsXyKernel 100 M points", 24, xy_n,
           lambda: capi.check(capi.lib().kmc_b200_pseudo_time_stamps_xy_device(x.data_ptr(), y.data_ptr(), ts.data_ptr(), xy_n, 0.0, 0.1, st)),
-          ["", "stamp_ctas=6", "stamp_ctas=4096"])
+          ["", "stamp_vec=1", "stamp_ctas=4", "stamp_ctas=5", "stamp_ctas=8", "stamp_ctas=4096", "stamp_ctas=3"])
     del x, y
     d_in = torch.empty((xy_n, 4), dtype=torch.float32, device="cuda")
     capi.synth_scans_device(d_in.data_ptr(), xy_n, 1, 128, 20110926, 0, st)

@@ -61,3 +61,56 @@ def test_random_batches_match_closed_form(capi, cuda, monkeypatch, sizes, seed, 
     if n:
         with capi.Handle(0, capacity) as h:
             assert h.deskew_batch(pts, offsets, params, mode=mode).tobytes() == out.tobytes()
+
+
+@settings(max_examples=30, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(sizes=SIZES, seed=st.integers(0, 2**31 - 1), capacity=st.sampled_from([64, 1000, 4096, 20_000, 250_000]),
+       memory=st.sampled_from(["pageable", "pinned", "pinned+16"]), zero_copy=st.booleans(), in_place=st.booleans(),
+       frame_call=st.booleans())
+def test_random_host_calls_match_the_device_result(capi, cuda, monkeypatch, sizes, seed, capacity, memory, zero_copy, in_place, frame_call):
+    """The host entry points over both transports (zero copy: the kernel reads / writes pinned memory itself; copy engines: the
+    three-slot H2D / kernel / D2H pipeline), pageable and pinned caller memory (also pinned memory that is only 16-byte aligned,
+    which switches the kernels to 128-bit accesses), in place and out of place, staging capacities far below and above the
+    batch: always the device entry point's bits, and nothing written outside the batch."""
+    torch = cuda
+    rng = np.random.default_rng(seed)
+    if frame_call:
+        sizes = [int(sum(sizes))]
+    n = int(sum(sizes))
+    if n == 0:
+        return
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    pts = helpers.synthetic_scan(n, 64, seed % 1000)
+    params = capi.params_array([capi.frame_params_from_twist(helpers.random_twist(rng), float(rng.uniform(0, 1))) for _ in sizes])
+    monkeypatch.setenv("KMC_B200_TUNE", "zc_points=100000000" if zero_copy else "zc_points=0")
+    d_in = torch.from_numpy(pts).cuda()
+    d_out = torch.empty_like(d_in)
+    capi.deskew_batch_device(d_in.data_ptr(), d_out.data_ptr(), torch.from_numpy(offsets).cuda().data_ptr(),
+                             torch.from_numpy(params.view(np.uint8)).cuda().data_ptr(), len(sizes), n, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = d_out.cpu().numpy()
+    guard = 8
+    shift = 1 if memory == "pinned+16" else 0
+
+    def buffer(fill):
+        if memory == "pageable":
+            whole = np.full((n + guard + 1, 4), fill, dtype=np.float32)
+            return whole, whole[shift:shift + n], whole.ctypes.data + 16 * shift
+        whole = torch.full((n + guard + 1, 4), fill, dtype=torch.float32).pin_memory()
+        return whole, whole.numpy()[shift:shift + n], whole.data_ptr() + 16 * shift
+
+    keep_in, view_in, ptr_in = buffer(0.0)
+    view_in[:] = pts
+    if in_place:
+        keep_out, view_out, ptr_out = keep_in, view_in, ptr_in
+    else:
+        keep_out, view_out, ptr_out = buffer(-77.0)
+    with capi.Handle(0, capacity) as h:
+        if frame_call:
+            h.deskew_frame_ptr(ptr_in, ptr_out, n, capi.FrameParams.from_buffer_copy(params[:1].tobytes()))
+        else:
+            h.deskew_batch_ptr(ptr_in, ptr_out, offsets, params)
+    assert view_out.tobytes() == want.tobytes(), (memory, zero_copy, in_place, capacity, sizes)
+    whole_out = keep_out if isinstance(keep_out, np.ndarray) else keep_out.numpy()
+    fill = 0.0 if in_place else -77.0
+    assert np.all(whole_out[:shift] == fill) and np.all(whole_out[shift + n:] == fill), "wrote outside the caller's buffer"

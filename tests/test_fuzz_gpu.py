@@ -85,8 +85,10 @@ def test_random_host_calls_match_the_device_result(capi, cuda, monkeypatch, size
     monkeypatch.setenv("KMC_B200_TUNE", "zc_points=100000000" if zero_copy else "zc_points=0")
     d_in = torch.from_numpy(pts).cuda()
     d_out = torch.empty_like(d_in)
-    capi.deskew_batch_device(d_in.data_ptr(), d_out.data_ptr(), torch.from_numpy(offsets).cuda().data_ptr(),
-                             torch.from_numpy(params.view(np.uint8)).cuda().data_ptr(), len(sizes), n, 0, torch.cuda.current_stream().cuda_stream)
+    d_off = torch.from_numpy(offsets).cuda()  # named: a temporary would be freed (and its block reused) before the kernel runs
+    d_par = torch.from_numpy(params.view(np.uint8)).cuda()
+    capi.deskew_batch_device(d_in.data_ptr(), d_out.data_ptr(), d_off.data_ptr(), d_par.data_ptr(), len(sizes), n, 0,
+                             torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     want = d_out.cpu().numpy()
     guard = 8

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define KMC_B200_VERSION 100 /* 0.1.0 */
+#define KMC_B200_VERSION 200 /* 0.2.0: round 2 — warnings (positive statuses), batch forms, checksums, file callback */
 
 #if defined(__GNUC__)
 #define KMC_B200_API __attribute__((visibility("default")))

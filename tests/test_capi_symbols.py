@@ -46,7 +46,7 @@ def test_header_compiles_as_plain_c():
 
 def test_version_and_status_strings(capi):
     lib = capi.lib()
-    assert lib.kmc_b200_version() == 100
+    assert lib.kmc_b200_version() == 200
     assert lib.kmc_b200_status_string(0) == b"ok"
     assert b"interval" in lib.kmc_b200_status_string(capi.ERR_TIME_OUT_OF_RANGE)
     assert C.sizeof(capi.FrameParams) == 64

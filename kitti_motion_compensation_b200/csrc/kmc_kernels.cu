@@ -441,7 +441,9 @@ __global__ void __launch_bounds__(kBlockThreads)
 // scheduler hands out (frame, lane) pairs in frame order.  The first version cut the flat point range into 4096-point items
 // as DeskewBatchKernel does; with nine streams per item that gave 4.3-5.5 TB/s against 6.6 for the single-frame kernel
 // (profiles/r02_sweep_f64_batch.log).  The frame's 64-byte record sits in shared memory: in registers it costs 16 of them on top of
-// nine 64-bit column pointers (79 registers, 3 CTAs per SM).
+// nine 64-bit column pointers (79 registers, 3 CTAs per SM).  Measured and not adopted: loading the next tile before computing the
+// current one (and the first tile before the record arrives) — 5 838-5 888 against 6 035-6 043 GB/s: 80 bytes in flight per thread
+// overshoot the sweet spot and the extra live values spill.
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 4)  // 64 registers, no spills, 4 CTAs of 256 threads per SM
     DeskewCloudF64BatchKernel(const double* __restrict__ cloud, const double* __restrict__ stamps, double* __restrict__ out,

@@ -168,9 +168,12 @@ class SharedPool {
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
-        if ((spins & 63) == 0 && std::chrono::steady_clock::now() > give_up) {
-          lock.lock();
-          break;
+        if ((spins & 63) == 0) {
+          if (std::chrono::steady_clock::now() > give_up) {
+            lock.lock();
+            break;
+          }
+          std::this_thread::yield();  // with as many callers as cores the pool's workers need the cores more than the spinners do
         }
       }
     }

@@ -409,25 +409,75 @@ __global__ void __launch_bounds__(BLOCK)
 // flags: bit 0 = a stamp outside [t1, t2] (the reference asserts), bit 1 = a 4th-column entry that is not 1 (honoured as
 // the reference does: R p + t w, w passed through — motion_compensation.cpp:13).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlockThreads)
-    DeskewCloudF64Kernel(const double* __restrict__ cloud, const double* __restrict__ stamps, double* __restrict__ out, int64_t n,
-                         double t1, double t2, double x_req, const __grid_constant__ kmc_b200_frame_params P,
-                         int* __restrict__ flags) {
-  int64_t const stride = static_cast<int64_t>(gridDim.x) * kBlockThreads;
-  double const duration = t2 - t1;
+__device__ __forceinline__ double2 LoadPairF64(const double* __restrict__ p, bool aligned16) {
+  if (aligned16) return __ldg(reinterpret_cast<const double2*>(p));
+  return make_double2(__ldg(p), __ldg(p + 1));
+}
+__device__ __forceinline__ void StorePairF64(double* __restrict__ p, bool aligned16, double a, double b) {
+  if (aligned16) {
+    // as PTX: written as a C++ double2 store, the compiler merges both branches into one STG.128 and faults on odd columns
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+  } else {
+    p[0] = a;
+    p[1] = b;
+  }
+}
+
+// One column-major N x 4 double matrix `c` with its stamps `ts` -> `o`, the points lane, lane + lanes, ... (PAIR: the point
+// PAIRS).  PAIR = two neighbouring points per thread with 128-bit accesses on every column that starts 16-byte aligned (all of
+// them when N is even; x and z always; a misaligned column falls back to two 64-bit accesses, uniformly per frame): twice the
+// bytes in flight per thread at the same residency, half the memory instructions — 6.6-6.8 TB/s against 5.9-6.0 for one point
+// per thread (profiles/r02_sweep_f64_batch_pair_defaults.log).  Returns the flag bits seen by this thread.
+template <bool PAIR, typename Params>
+__device__ __forceinline__ int DeskewF64Columns(const double* __restrict__ c, const double* __restrict__ ts, double* __restrict__ o,
+                                                int64_t n, int64_t lane, int64_t lanes, double t1, double t2, double duration,
+                                                double x_req, const Params& P) {
   int bad = 0;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x; i < n; i += stride) {
-    double const x = __ldg(cloud + i), y = __ldg(cloud + n + i), z = __ldg(cloud + 2 * n + i), w = __ldg(cloud + 3 * n + i);
-    double const t = __ldg(stamps + i);
+  auto one = [&](int64_t i) {
+    double const x = __ldg(c + i), y = __ldg(c + n + i), z = __ldg(c + 2 * n + i), w = __ldg(c + 3 * n + i);
+    double const t = __ldg(ts + i);
     if (!(t >= t1 && t <= t2)) bad |= 1;
     if (w != 1.0) bad |= 2;
     float const s = static_cast<float>((t - t1) / duration - x_req);  // FractionOfTrajectory, trajectory_interpolation.cpp:49-51
     float3 const d = DeskewDeltaW(static_cast<float>(x), static_cast<float>(y), static_cast<float>(z), static_cast<float>(w), s, P);
-    out[i] = x + static_cast<double>(d.x);
-    out[n + i] = y + static_cast<double>(d.y);
-    out[2 * n + i] = z + static_cast<double>(d.z);
-    out[3 * n + i] = w;
+    o[i] = x + static_cast<double>(d.x);
+    o[n + i] = y + static_cast<double>(d.y);
+    o[2 * n + i] = z + static_cast<double>(d.z);
+    o[3 * n + i] = w;
+  };
+  if constexpr (!PAIR) {
+    for (int64_t i = lane; i < n; i += lanes) one(i);
+  } else {
+    // i is even, so a column is 16-byte aligned at i exactly when its first element is
+    auto const al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    bool const ax = al(c) && al(o), ay = al(c + n) && al(o + n), az = al(c + 2 * n) && al(o + 2 * n), aw = al(c + 3 * n) && al(o + 3 * n);
+    bool const at = al(ts);
+    int64_t i = 2 * lane;
+    for (; i + 1 < n; i += 2 * lanes) {
+      double2 const x = LoadPairF64(c + i, ax), y = LoadPairF64(c + n + i, ay), z = LoadPairF64(c + 2 * n + i, az);
+      double2 const w = LoadPairF64(c + 3 * n + i, aw), t = LoadPairF64(ts + i, at);
+      if (!(t.x >= t1 && t.x <= t2) || !(t.y >= t1 && t.y <= t2)) bad |= 1;
+      if (w.x != 1.0 || w.y != 1.0) bad |= 2;
+      float const s0 = static_cast<float>((t.x - t1) / duration - x_req), s1 = static_cast<float>((t.y - t1) / duration - x_req);
+      float3 const d0 = DeskewDeltaW(static_cast<float>(x.x), static_cast<float>(y.x), static_cast<float>(z.x), static_cast<float>(w.x), s0, P);
+      float3 const d1 = DeskewDeltaW(static_cast<float>(x.y), static_cast<float>(y.y), static_cast<float>(z.y), static_cast<float>(w.y), s1, P);
+      StorePairF64(o + i, ax, x.x + static_cast<double>(d0.x), x.y + static_cast<double>(d1.x));
+      StorePairF64(o + n + i, ay, y.x + static_cast<double>(d0.y), y.y + static_cast<double>(d1.y));
+      StorePairF64(o + 2 * n + i, az, z.x + static_cast<double>(d0.z), z.y + static_cast<double>(d1.z));
+      StorePairF64(o + 3 * n + i, aw, w.x, w.y);
+    }
+    if (i < n) one(i);  // the odd last point
   }
+  return bad;
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(kBlockThreads, PAIR ? 4 : 1)
+    DeskewCloudF64Kernel(const double* __restrict__ cloud, const double* __restrict__ stamps, double* __restrict__ out, int64_t n,
+                         double t1, double t2, double x_req, const __grid_constant__ kmc_b200_frame_params P,
+                         int* __restrict__ flags) {
+  int const bad = DeskewF64Columns<PAIR>(cloud, stamps, out, n, static_cast<int64_t>(blockIdx.x) * kBlockThreads + threadIdx.x,
+                                         static_cast<int64_t>(gridDim.x) * kBlockThreads, t1, t2, t2 - t1, x_req, P);
   if (bad) atomicOr(flags, bad);
 }
 
@@ -441,20 +491,22 @@ __global__ void __launch_bounds__(kBlockThreads)
 // scheduler hands out (frame, lane) pairs in frame order.  The first version cut the flat point range into 4096-point items
 // as DeskewBatchKernel does; with nine streams per item that gave 4.3-5.5 TB/s against 6.6 for the single-frame kernel
 // (profiles/r02_sweep_f64_batch.log).  The frame's 64-byte record sits in shared memory: in registers it costs 16 of them on top of
-// nine 64-bit column pointers (79 registers, 3 CTAs per SM).  Measured and not adopted: loading the next tile before computing the
-// current one (and the first tile before the record arrives) — 5 838-5 888 against 6 035-6 043 GB/s: 80 bytes in flight per thread
-// overshoot the sweet spot and the extra live values spill.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 4)  // 64 registers, no spills, 4 CTAs of 256 threads per SM
+// nine 64-bit column pointers.  One point per thread this shape ran at 5.97-6.06 TB/s (64 registers, 1024 threads per SM, 40 bytes
+// in flight per thread); two points per thread (DeskewF64Columns<true>, still 64 registers) 6.6-6.8 TB/s for every frame shape
+// from one 39 M-point frame to 3000 frames of 13 001 points (profiles/r02_sweep_f64_batch_pair_defaults.log).  Measured and not adopted:
+// loading the next tile before computing the current one — slower, the extra live values spill.
+template <int BLOCK, bool PAIR, int MIN_CTAS>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS)
     DeskewCloudF64BatchKernel(const double* __restrict__ cloud, const double* __restrict__ stamps, double* __restrict__ out,
                               const int64_t* __restrict__ offsets, const kmc_b200_frame_params* __restrict__ table,
                               const double* __restrict__ times, int n_frames, int* __restrict__ flags) {
   __shared__ kmc_b200_frame_params record;
+  constexpr int PER = PAIR ? 2 : 1;
   int const f = static_cast<int>(blockIdx.y) + static_cast<int>(blockIdx.z) * static_cast<int>(gridDim.y);
   if (f >= n_frames) return;
   int64_t const frame_begin = __ldg(offsets + f);
   int64_t const nf = __ldg(offsets + f + 1) - frame_begin;
-  if (static_cast<int64_t>(blockIdx.x) * BLOCK >= nf) return;  // more CTAs per frame than this frame has tiles
+  if (static_cast<int64_t>(blockIdx.x) * BLOCK * PER >= nf) return;  // more CTAs per frame than this frame has tiles
   if (threadIdx.x < 16) reinterpret_cast<float*>(&record)[threadIdx.x] = __ldg(reinterpret_cast<const float*>(table + f) + threadIdx.x);
   double const t1 = __ldg(times + 3 * f), t2 = __ldg(times + 3 * f + 1), t_req = __ldg(times + 3 * f + 2);
   __syncthreads();
@@ -463,20 +515,8 @@ __global__ void __launch_bounds__(BLOCK, 4)  // 64 registers, no spills, 4 CTAs 
   const double* const c = cloud + 4 * frame_begin;
   double* const o = out + 4 * frame_begin;
   const double* const ts = stamps + frame_begin;
-  int64_t const stride = static_cast<int64_t>(gridDim.x) * BLOCK;
-  int bad = 0;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * BLOCK + threadIdx.x; i < nf; i += stride) {
-    double const x = __ldg(c + i), y = __ldg(c + nf + i), z = __ldg(c + 2 * nf + i), w = __ldg(c + 3 * nf + i);
-    double const t = __ldg(ts + i);
-    if (!(t >= t1 && t <= t2)) bad |= 1;
-    if (w != 1.0) bad |= 2;
-    float const s = static_cast<float>((t - t1) / duration - x_req);
-    float3 const d = DeskewDeltaW(static_cast<float>(x), static_cast<float>(y), static_cast<float>(z), static_cast<float>(w), s, record);
-    o[i] = x + static_cast<double>(d.x);
-    o[nf + i] = y + static_cast<double>(d.y);
-    o[2 * nf + i] = z + static_cast<double>(d.z);
-    o[3 * nf + i] = w;
-  }
+  int const bad = DeskewF64Columns<PAIR>(c, ts, o, nf, static_cast<int64_t>(blockIdx.x) * BLOCK + threadIdx.x,
+                                         static_cast<int64_t>(gridDim.x) * BLOCK, t1, t2, duration, x_req, record);
   if (bad) atomicOr(flags + f, bad);
 }
 
@@ -1072,15 +1112,25 @@ cudaError_t LaunchDeskewCloudF64Batch(const double* cloud, const double* stamps,
   cudaError_t e = cudaMemsetAsync(flags_dev, 0, static_cast<size_t>(n_frames) * sizeof(int), stream);
   if (e != cudaSuccess || n_points <= 0) return e;
   // gridDim.x CTAs share a frame: enough of them that each strides over ~f64_item_tiles tiles of an average frame
+  // (KITTI-size and larger frames: 2 tiles of 512 points, 6.70-6.81 TB/s; small frames want 4: 6.65 against 6.30 at 13 001 points)
   int const block = kmc_b200::internal::TuneValue("f64_block", 256) == 128 ? 128 : 256;
-  int64_t const tiles = std::max(1, kmc_b200::internal::TuneValue("f64_item_tiles", 16));
   int64_t const avg = (n_points + n_frames - 1) / n_frames;
-  unsigned const gx = static_cast<unsigned>(std::min<int64_t>(std::max<int64_t>((avg + block * tiles - 1) / (block * tiles), 1), 65535));
+  int64_t const tiles = std::max(1, kmc_b200::internal::TuneValue("f64_item_tiles", avg >= 65536 ? 2 : 4));
+  bool const pair = kmc_b200::internal::TuneValue("f64_pair", 1) != 0;
+  int const min_ctas = kmc_b200::internal::TuneValue("f64_min_ctas", 4);
+  int64_t const per_cta = static_cast<int64_t>(block) * (pair ? 2 : 1) * tiles;
+  unsigned const gx = static_cast<unsigned>(std::min<int64_t>(std::max<int64_t>((avg + per_cta - 1) / per_cta, 1), 65535));
   unsigned const gy = static_cast<unsigned>(std::min<int32_t>(n_frames, 32768));
   unsigned const gz = static_cast<unsigned>((n_frames + static_cast<int32_t>(gy) - 1) / static_cast<int32_t>(gy));
   dim3 const grid(gx, gy, gz);
-  if (block == 128) DeskewCloudF64BatchKernel<128><<<grid, 128, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, flags_dev);
-  else DeskewCloudF64BatchKernel<256><<<grid, 256, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, flags_dev);
+#define KMC_F64B(BLOCK, PAIR, MIN) DeskewCloudF64BatchKernel<BLOCK, PAIR, MIN><<<grid, BLOCK, 0, stream>>>(cloud, stamps, out, offsets_dev, params_dev, times_dev, n_frames, flags_dev)
+  if (pair) {
+    if (block == 128) { if (min_ctas == 8) KMC_F64B(128, true, 8); else KMC_F64B(128, true, 6); }
+    else { if (min_ctas == 4) KMC_F64B(256, true, 4); else KMC_F64B(256, true, 3); }
+  } else {
+    if (block == 128) KMC_F64B(128, false, 4); else KMC_F64B(256, false, 4);
+  }
+#undef KMC_F64B
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
@@ -1103,11 +1153,21 @@ cudaError_t LaunchPseudoTimeStamps(const float* in, double* stamps, int64_t n, d
 cudaError_t LaunchDeskewCloudF64(const double* cloud, const double* stamps, double* out, int64_t n, double t1, double t2, double x_req,
                                  const kmc_b200_frame_params& params, int* flags_dev, int sm_count, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
-  // 8 x 256 threads per SM (full residency): 6 587 GB/s; 6 x 256: 5 886; one CTA per tile: 6 258 (profiles/r02_sweep_secondary.log)
-  int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("f64_ctas", 8));
-  if (grid > cap) grid = cap;
-  DeskewCloudF64Kernel<<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(cloud, stamps, out, n, t1, t2, x_req, params, flags_dev);
+  // two points per thread, one CTA per tile of 512 points: 6.90 TB/s (2 tiles 6.78, 4 tiles 6.67, persistent 8 CTAs per SM 6.18;
+  // the one-point kernel, f64_pair=0, persistent at 8 x 256 threads per SM: 6.43-6.59 — profiles/r02_sweep_f64_batch_pair_defaults.log)
+  bool const pair = kmc_b200::internal::TuneValue("f64_pair", 1) != 0;
+  if (pair) {
+    int64_t const per_cta = static_cast<int64_t>(kBlockThreads) * 2 * std::max(1, kmc_b200::internal::TuneValue("f64_item_tiles", 1));
+    int64_t grid = (n + per_cta - 1) / per_cta;
+    int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("f64_ctas", 4096));
+    if (grid > cap) grid = cap;
+    DeskewCloudF64Kernel<true><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(cloud, stamps, out, n, t1, t2, x_req, params, flags_dev);
+  } else {
+    int64_t grid = (n + kBlockThreads - 1) / kBlockThreads;
+    int64_t const cap = static_cast<int64_t>(sm_count) * std::max(1, kmc_b200::internal::TuneValue("f64_ctas", 8));
+    if (grid > cap) grid = cap;
+    DeskewCloudF64Kernel<false><<<static_cast<unsigned>(grid), kBlockThreads, 0, stream>>>(cloud, stamps, out, n, t1, t2, x_req, params, flags_dev);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

@@ -162,6 +162,62 @@ def test_f64_batch_device_equals_per_frame_and_the_reference(capi, oracle, cuda)
         assert np.array_equal(got[:, 3], c[:, 3])
 
 
+@pytest.mark.parametrize("shift", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)])
+def test_f64_kernels_two_points_per_thread_equal_one_point_per_thread(capi, oracle, cuda, monkeypatch, shift):
+    """The f64 kernels take two points per thread with 128-bit accesses on every 16-byte-aligned column and 64-bit accesses on
+    the others.  Every mix of alignments — odd frame sizes, odd frame starts, cloud / stamps / result pointers that are only
+    8-byte aligned — gives the bits of the one-point-per-thread kernels (KMC_B200_TUNE f64_pair=0), for the batch and the
+    single-frame entry point, and nothing is written outside the result block."""
+    torch = cuda
+    sizes = [2, 3, 1, 0, 511, 512, 513, 1_025, 40_000, 12_345, 130_001, 6]
+    pts, offsets, frames, times, cloud, stamps, per_frame = f64_batch_inputs(oracle, sizes, 811)
+    F, n = len(sizes), len(pts)
+    params = capi.params_array([capi.frame_params_from_poses(Ts, Te, times[f, 0], times[f, 1], times[f, 2]) for f, (Ts, Te, _, _) in enumerate(frames)])
+    st = torch.cuda.current_stream().cuda_stream
+    sc, ss, so = shift
+    d_cloud_buf, d_stamps_buf = torch.zeros(4 * n + 2, dtype=torch.float64, device="cuda"), torch.zeros(n + 2, dtype=torch.float64, device="cuda")
+    d_cloud, d_stamps = d_cloud_buf[sc:sc + 4 * n], d_stamps_buf[ss:ss + n]
+    d_cloud.copy_(torch.from_numpy(cloud))
+    d_stamps.copy_(torch.from_numpy(stamps))
+    d_off, d_par, d_times = dev(torch, offsets), dev(torch, params.view(np.uint8)), dev(torch, times.reshape(-1))
+    d_flags = torch.zeros(F, dtype=torch.int32, device="cuda")
+    results = {}
+    for pair in (0, 1):
+        monkeypatch.setenv("KMC_B200_TUNE", f"f64_pair={pair}")
+        buf = torch.full((4 * n + 2,), -7.0, dtype=torch.float64, device="cuda")
+        d_out = buf[so:so + 4 * n]
+        capi.deskew_cloud_f64_batch_device(d_cloud.data_ptr(), d_stamps.data_ptr(), d_out.data_ptr(), d_off.data_ptr(), d_par.data_ptr(),
+                                           d_times.data_ptr(), F, n, d_flags.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert d_flags.cpu().tolist() == [0] * F
+        whole = buf.cpu().numpy()
+        assert np.all(whole[:so] == -7.0) and np.all(whole[so + 4 * n:] == -7.0)
+        single = torch.full((4 * n + 2,), -7.0, dtype=torch.float64, device="cuda")
+        one_flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for f in range(F):
+            a, b = int(offsets[f]), int(offsets[f + 1])
+            if a == b:
+                continue
+            p = capi.FrameParams.from_buffer_copy(params[f:f + 1].tobytes())
+            capi.check(capi.lib().kmc_b200_deskew_cloud_f64_device(d_cloud[4 * a:].data_ptr(), d_stamps[a:].data_ptr(), single[so + 4 * a:].data_ptr(),
+                                                                    b - a, times[f, 0], times[f, 1], times[f, 2], C.byref(p), one_flag.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert int(one_flag.item()) == 0
+        results[pair] = (whole[so:so + 4 * n].copy(), single.cpu().numpy()[so:so + 4 * n].copy())
+        assert np.array_equal(results[pair][0], results[pair][1])
+    assert np.array_equal(results[0][0].view(np.int64), results[1][0].view(np.int64))
+    # and the values are the reference's (largest frame)
+    f = sizes.index(130_001)
+    a, b = int(offsets[f]), int(offsets[f + 1])
+    Ts, Te, _, _ = frames[f]
+    c, ts = per_frame[f]
+    engine = rb if rb.available() else oracle
+    ref = engine.motion_compensate_frame(c, ts, Ts, Te, times[f, 0], times[f, 1], times[f, 2])
+    got = results[1][0][4 * a:4 * b].reshape(4, b - a).T
+    disp = float(np.abs(ref[:, :3] - c[:, :3]).max())
+    assert np.abs(got[:, :3] - ref[:, :3]).max() < 2e-7 + 4e-7 * disp
+
+
 def test_f64_batch_host_equals_single_frame_host_calls(capi, oracle, cuda):
     sizes = [123_397, 0, 5, 70_001, 9_000]
     _, _, frames, times, _, _, per_frame = f64_batch_inputs(oracle, sizes, 5400)

@@ -378,6 +378,12 @@ kmc_b200::dev::LaunchConfig PickHostCallConfig(const kmc_b200_handle* h, int64_t
     cfg.vec = (TuneValue("zc_vec", 1) == 2 && aligned32) ? 2 : 1;
     cfg.item_tiles = std::max(1, TuneValue("zc_tiles", 4));  // 70.9-71.3 us vs 72.5-73.3 with 1 tile; every other shape 71-86 (profiles/r02_sweep_single_scan_fine.log)
     if (cfg.block != 128 && cfg.block != 512) cfg.block = 256;
+    if (TuneValue("zc_bulk", 0) == 1) {  // experiment: TMA bulk copies straight from / to the pinned host buffers
+      cfg.bulk = 1;
+      cfg.block = cfg.block == 128 ? 128 : 256;
+      cfg.unroll = TuneValue("zc_unroll", 2);
+      cfg.stages = TuneValue("zc_stages", 3);
+    }
   } else {
     cudaGetLastError();
   }

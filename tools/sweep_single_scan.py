@@ -56,6 +56,11 @@ def main():
         print(s, flush=True)
         lines.append(s)
 
+    if len(sys.argv) > 1:  # python tools/sweep_single_scan.py "tune a;tune b" [sizes]
+        sizes = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [130_000]
+        for tune in sys.argv[1].split(";"):
+            log(f"{tune or 'default':52s} {json.dumps(run(tune, sizes))}")
+        return
     log("== one 130 000-point scan, zero-copy shape sweep (us, median of 300) ==")
     for tune in ["", "zc_tiles=4", "zc_tiles=2", "zc_unroll=2", "zc_unroll=2,zc_tiles=2", "zc_hint=1", "zc_hint=1,zc_tiles=4", "zc_block=512", "zc_block=512,zc_tiles=2",
                  "zc_block=128,zc_ctas=2,zc_tiles=4", "zc_ctas=2,zc_tiles=4", "", "zc_tiles=4", "zc_tiles=8", "zc_unroll=2,zc_tiles=4", "zc_points=0"]:

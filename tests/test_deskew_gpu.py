@@ -548,6 +548,53 @@ def test_large_batch_properties_and_spot_parity(capi, oracle, cuda):
     assert float((fwd[:, :3] - d_in[:, :3]).abs().max()) < 3e-5  # two float32 roundings at up to 120 m + 2 x 1e-7 x |displacement|
 
 
+def test_full_size_retarget_and_rigidity_properties(capi, oracle, cuda):
+    """Two size-independent properties of the deskew over a bandwidth-sized batch (1 000 x 130 000 points), every point checked:
+    * re-targeting: with p'_a = Exp((x_i - a) xi) p and p'_b = Exp((x_i - b) xi) p (motion_compensation.cpp:16-28 with two
+      requested times), p'_b = Exp((a - b) xi) p'_a — ONE rigid transform per frame maps the result for one requested time
+      onto the result for another (evaluated here in double by torch from the oracle's Exp);
+    * rigidity: points that share a stamp move by the same rigid transform, so their mutual distances survive the deskew
+      (FROM_W mode, neighbouring points given equal fractions)."""
+    torch = cuda
+    n, scans, a, b = 130_000, 1_000, 0.5, 0.125
+    params_a, xi = capi.synth_frame_params(scans, 31415, 0, a)
+    params_b, xi_b = capi.synth_frame_params(scans, 31415, 0, b)
+    assert np.array_equal(xi, xi_b)
+    d_in = torch.empty((scans * n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(d_in.data_ptr(), n, scans, 64, 31415, 0)
+    d_off = torch.arange(0, (scans + 1) * n, n, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    out_a, out_b = torch.empty_like(d_in), torch.empty_like(d_in)
+    capi.deskew_batch_device(d_in.data_ptr(), out_a.data_ptr(), d_off.data_ptr(), dev(torch, params_a.view(np.uint8)).data_ptr(), scans, scans * n, 0, stream)
+    capi.deskew_batch_device(d_in.data_ptr(), out_b.data_ptr(), d_off.data_ptr(), dev(torch, params_b.view(np.uint8)).data_ptr(), scans, scans * n, 0, stream)
+    torch.cuda.synchronize()
+    M = np.stack([oracle.se3_exp((a - b) * xi[f]) for f in range(scans)])
+    R, t = torch.from_numpy(M[:, :3, :3].copy()).cuda(), torch.from_numpy(M[:, :3, 3].copy()).cuda()
+    worst = 0.0
+    for f0 in range(0, scans, 100):  # 100 frames at a time: 13 M points x 3 doubles
+        pa = out_a[f0 * n:(f0 + 100) * n, :3].double().reshape(100, n, 3)
+        mapped = torch.einsum("fij,fnj->fni", R[f0:f0 + 100], pa) + t[f0:f0 + 100, None, :]
+        worst = max(worst, float((mapped - out_b[f0 * n:(f0 + 100) * n, :3].double().reshape(100, n, 3)).abs().max()))
+    print(f"re-targeting over {scans * n} points: max |Exp((a-b) xi) p'_a - p'_b| = {worst:.3e} m")
+    assert worst < 1.2e-5  # two independent float32 results at up to 120 m (3.8e-6 each) + 2 x 2.5e-7 x |displacement|
+    assert float((out_a[:, :3] - out_b[:, :3]).abs().max()) > 0.05  # the two requested times do differ
+    del out_b, mapped, pa
+    # rigidity: pairs (2k, 2k+1) share the fraction of point 2k
+    az = torch.atan2(d_in[0::2, 1].double(), d_in[0::2, 0].double())
+    frac = ((np.pi - az) / (2 * np.pi)).float()
+    d_in[0::2, 3] = frac
+    d_in[1::2, 3] = frac
+    del az, frac
+    capi.deskew_batch_device(d_in.data_ptr(), out_a.data_ptr(), d_off.data_ptr(), dev(torch, params_a.view(np.uint8)).data_ptr(), scans, scans * n, 1, stream)
+    torch.cuda.synchronize()
+    before = (d_in[0::2, :3].double() - d_in[1::2, :3].double()).norm(dim=1)
+    after = (out_a[0::2, :3].double() - out_a[1::2, :3].double()).norm(dim=1)
+    drift = float((before - after).abs().max())
+    print(f"rigidity over {scans * n // 2} pairs: max | |p_i - p_j| - |p'_i - p'_j| | = {drift:.3e} m")
+    assert drift < 1.6e-5  # each of the two results is rounded to float32 per coordinate (<= 3.8e-6 at 64-128 m): 2 x sqrt(3) x 3.8e-6 + the fp32 model error
+    assert torch.equal(out_a[:, 3], d_in[:, 3])
+
+
 def test_config5_dense_10m_point_frame(capi, oracle, cuda):
     """BASELINE config 5: one dense 128-beam frame of 10 M points (128 rings x 78 125 azimuth steps).  Parity against the
     oracle on 1 % of the points plus 64 points either side of EVERY ring boundary and the frame's head and tail,

@@ -77,7 +77,7 @@ typedef enum kmc_b200_time_mode {
 } kmc_b200_time_mode;
 
 /* Per-frame constants of the fused kernel: 64 bytes, computed once per frame on the host in double and rounded to
- * float.  With xi = [rho; phi] = Log(T_start^-1 T_end), theta = |phi|, a = phi/theta (0 if theta == 0):
+ * float.  With xi = [rho; phi] = Log(T_start^-1 T_end), theta = |phi|, a = phi/theta (0 if theta < 1e-12):
  *   phi[3], theta2 = theta^2
  *   rho_perp[3] = rho - a (a.rho),  c0 = 0.5 - x_req          (FROM_AZIMUTH: s = c0 - atan2(y,x)/2pi)
  *   rho_par[3]  = a (a.rho),        x_req = (t_req - t_start)/(t_end - t_start)   (FROM_W: s = w - x_req)

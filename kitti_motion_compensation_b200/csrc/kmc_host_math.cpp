@@ -242,7 +242,10 @@ void FrameParamsFromTwist(const double xi[6], double x_req, kmc_b200_frame_param
   double const th2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
   double const th = std::sqrt(th2);
   double par[3] = {0, 0, 0};
-  if (th > 0.0) {
+  // Below 1e-12 rad per scan the rotation moves a point at 120 m by 1e-10 m and phi is rounding noise of the pose product
+  // (a pure translation between two Mercator-magnitude poses leaves |phi| ~ 1e-17): no axis, the whole of rho goes to rho_perp,
+  // so the record of a pure translation does not depend on where on the globe the frame sits.
+  if (th2 > 1e-24) {
     double const k = (phi[0] * rho[0] + phi[1] * rho[1] + phi[2] * rho[2]) / th2;  // (a.rho)/theta
     for (int i = 0; i < 3; ++i) par[i] = k * phi[i];
   }

@@ -154,7 +154,7 @@ def lib() -> C.CDLL:
 
 
 def last_error() -> str:
-    return lib().kmc_b200_last_error().decode()
+    return lib().kmc_b200_last_error().decode(errors="replace")  # messages may quote bytes of a corrupt input file
 
 
 last_warning = 0  # the most recent positive (warning) status seen by check()

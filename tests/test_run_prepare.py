@@ -107,3 +107,71 @@ def test_error_statuses(capi, tmp_path):
         (w / "velodyne_points" / "timestamps_start.txt").write_text("\n".join(lines) + "\n")
     err = broken(out_of_range)
     assert err.status == capi.ERR_TIME_OUT_OF_RANGE and "frame 3" in str(err)
+
+
+def test_corrupt_run_folders_give_a_status_never_a_crash(capi, tmp_path):
+    """The reference parses the run's text files with std::stoi / stod / getline and throws or aborts on garbage
+    (data_io.cpp:18-99).  kmc_b200_run_prepare must return: OK with finite records, or a negative status — never crash, hang
+    or hand back NaN records — whatever one of the text files holds.  Random byte strings, truncations, line-level edits and
+    number-level edits of each of the five kinds of text file, drawn by hypothesis (deterministic)."""
+    import ctypes as C
+
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    n = 6
+    run = tmp_path / "run_sync"
+    helpers.make_run_folder(str(run), n, 10, seed=21)
+    targets = ["velodyne_points/timestamps_start.txt", "velodyne_points/timestamps.txt", "velodyne_points/timestamps_end.txt",
+               "oxts/timestamps.txt", "oxts/data/0000000002.txt"]
+    originals = {t: (run / t).read_bytes() for t in targets}
+    tokens = st.sampled_from([b"nan", b"inf", b"-inf", b"1e999", b"-", b"", b" ", b"\x00", b"25:61:61.5", b"ab:cd:12.3", b"13:04", b"::",
+                              b"9" * 400, b"0x10", b"1,5", b"\xff\xfe", b"2011-09-26 13:04:32.123456789", b"2011-09-26"])
+
+    def mutate(data: bytes, kind: int, pos: float, token: bytes, blob: bytes) -> bytes:
+        lines = data.split(b"\n")
+        k = min(int(pos * len(lines)), len(lines) - 1)
+        if kind == 0:
+            return blob  # arbitrary bytes
+        if kind == 1:
+            return data[: int(pos * len(data))]  # truncated
+        if kind == 2:
+            lines[k] = token  # one line replaced
+        elif kind == 3:
+            fields = lines[k].split(b" ")
+            fields[min(int(pos * 7919) % max(len(fields), 1), len(fields) - 1)] = token  # one field replaced
+            lines[k] = b" ".join(fields)
+        elif kind == 4:
+            del lines[k]  # one line missing
+        else:
+            lines.insert(k, token)  # one line too many
+        return b"\n".join(lines)
+
+    params = np.zeros(n, dtype=capi.FRAME_PARAMS_DTYPE)
+    count = C.c_int64()
+    seen = set()
+
+    @settings(max_examples=400, deadline=None, database=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(which=st.integers(0, len(targets) - 1), kind=st.integers(0, 5), pos=st.floats(0, 1, exclude_max=True), token=tokens,
+           blob=st.binary(max_size=300))
+    def run_one(which, kind, pos, token, blob):
+        target = targets[which]
+        (run / target).write_bytes(mutate(originals[target], kind, pos, token, blob))
+        try:
+            count.value = -1
+            rc = capi.lib().kmc_b200_run_prepare(os.fsencode(str(run)), n, params.ctypes.data, C.byref(count))
+        finally:
+            (run / target).write_bytes(originals[target])
+        seen.add(rc)
+        assert rc <= 1, rc  # OK, a warning, or an error status
+        if rc >= 0:
+            assert count.value == n
+            rec = params[: n - 2].view(np.float32)
+            assert np.all(np.isfinite(rec)), (target, kind, token)
+        else:
+            assert capi.last_error() != ""
+
+    run_one()
+    assert capi.OK in seen and any(rc < 0 for rc in seen)  # both outcomes were exercised
+    n_frames, _ = capi.run_prepare(str(run))  # the restored folder still parses
+    assert n_frames == n

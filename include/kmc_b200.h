@@ -201,7 +201,9 @@ KMC_B200_API int kmc_b200_deskew_batch_device(const float* xyzi_in, float* xyzi_
  * carries no float32 output rounding.  The 4th column is honoured as the reference does (Affine3d * Vector4d,
  * motion_compensation.cpp:13): p' = R p + t w, w passed through.  flags_dev (device int, caller-zeroed) receives bit 0 if
  * any stamp lies outside [t_start, t_end] (where the reference asserts) and bit 1 if a 4th-column entry is not the
- * homogeneous 1 (informational).  x_req = (t_req - t_start)/(t_end - t_start) must be the value params was built with. */
+ * homogeneous 1 (informational).  x_req = (t_req - t_start)/(t_end - t_start) must be the value params was built with.
+ * out_colmajor may be cloud_colmajor itself (in place); any other overlap is not allowed.  Pointers need 8-byte alignment only
+ * (16-byte aligned columns are moved with 128-bit accesses). */
 KMC_B200_API int kmc_b200_deskew_cloud_f64_device(const double* cloud_colmajor, const double* stamps, double* out_colmajor,
                                                   int64_t n_points, double t_start, double t_end, double t_req,
                                                   const kmc_b200_frame_params* params_host, int* flags_dev, void* stream);

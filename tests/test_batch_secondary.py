@@ -206,6 +206,12 @@ def test_f64_kernels_two_points_per_thread_equal_one_point_per_thread(capi, orac
         results[pair] = (whole[so:so + 4 * n].copy(), single.cpu().numpy()[so:so + 4 * n].copy())
         assert np.array_equal(results[pair][0], results[pair][1])
     assert np.array_equal(results[0][0].view(np.int64), results[1][0].view(np.int64))
+    # in place (out == cloud): every thread reads its own points before it writes them
+    in_place = d_cloud.clone() if sc == 0 else d_cloud_buf.clone()[sc:sc + 4 * n]
+    capi.deskew_cloud_f64_batch_device(in_place.data_ptr(), d_stamps.data_ptr(), in_place.data_ptr(), d_off.data_ptr(), d_par.data_ptr(),
+                                       d_times.data_ptr(), F, n, d_flags.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert np.array_equal(in_place.cpu().numpy(), results[1][0])
     # and the values are the reference's (largest frame)
     f = sizes.index(130_001)
     a, b = int(offsets[f]), int(offsets[f + 1])

@@ -595,6 +595,36 @@ def test_full_size_retarget_and_rigidity_properties(capi, oracle, cuda):
     assert torch.equal(out_a[:, 3], d_in[:, 3])
 
 
+def test_back_to_back_frame_launches_keep_stream_order(capi, cuda):
+    """The single-frame kernel is launched with programmatic stream serialization (its CTAs may become resident while the
+    previous kernel of the stream drains; griddepcontrol.wait holds them until that kernel has completed).  A dependent chain on
+    one stream — 40 in-place launches alternating xi and -xi, each reading what the previous one wrote, behind a torch kernel
+    that produces the input — must give the bits of the same chain with a device synchronisation after every step."""
+    torch = cuda
+    n = 3_000_000  # 48 MB: several waves, a tail that overlaps the next launch
+    src = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    capi.synth_scans_device(src.data_ptr(), n, 1, 64, 99, 0)
+    xi = np.array([1.5, -0.05, 0.02, 0.003, -0.004, 0.05])
+    fwd, bwd = capi.frame_params_from_twist(xi, 0.5), capi.frame_params_from_twist(-xi, 0.25)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def chain(sync_every_step):
+        buf = torch.empty_like(src)
+        torch.cuda.synchronize()
+        buf.copy_(src)  # a kernel of another library writes the input; no synchronisation before the first launch
+        for k in range(40):
+            capi.deskew_frame_device(buf.data_ptr(), buf.data_ptr(), n, fwd if k % 2 == 0 else bwd, 0, stream)
+            if sync_every_step:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return buf
+
+    serial = chain(True)
+    for _ in range(3):
+        assert torch.equal(chain(False).view(torch.int32), serial.view(torch.int32))
+    assert not torch.equal(serial, src)
+
+
 def test_config5_dense_10m_point_frame(capi, oracle, cuda):
     """BASELINE config 5: one dense 128-beam frame of 10 M points (128 rings x 78 125 azimuth steps).  Parity against the
     oracle on 1 % of the points plus 64 points either side of EVERY ring boundary and the frame's head and tail,

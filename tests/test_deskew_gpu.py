@@ -624,6 +624,26 @@ def test_back_to_back_frame_launches_keep_stream_order(capi, cuda):
         assert torch.equal(chain(False).view(torch.int32), serial.view(torch.int32))
     assert not torch.equal(serial, src)
 
+    # the sharpest case: a small second launch that reads exactly what the LAST wave of the first one writes (its CTAs can be
+    # resident before that wave has finished; without griddepcontrol.wait this reads the zeros below — checked by removing it)
+    m = 60_000
+    mid, last = torch.empty_like(src), torch.empty((m, 4), dtype=torch.float32, device="cuda")
+
+    def tail(sync_between):
+        mid.zero_()
+        last.zero_()
+        torch.cuda.synchronize()
+        capi.deskew_frame_device(src.data_ptr(), mid.data_ptr(), n, fwd, 0, stream)
+        if sync_between:
+            torch.cuda.synchronize()
+        capi.deskew_frame_device(mid[n - m:].data_ptr(), last.data_ptr(), m, bwd, 0, stream)
+        torch.cuda.synchronize()
+        return last.clone()
+
+    want = tail(True)
+    for _ in range(20):
+        assert torch.equal(tail(False).view(torch.int32), want.view(torch.int32))
+
 
 def test_config5_dense_10m_point_frame(capi, oracle, cuda):
     """BASELINE config 5: one dense 128-beam frame of 10 M points (128 rings x 78 125 azimuth steps).  Parity against the

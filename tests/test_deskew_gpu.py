@@ -725,6 +725,45 @@ def test_accuracy_domain_at_long_range(capi, oracle, cuda, max_range, twist):
         assert np.array_equal(out[:, 3], pts[:, 3])
 
 
+def test_accuracy_model_over_random_frames(capi, cuda):
+    """The ACCURACY DOMAIN statement of include/kmc_b200.h over 60 seeded random frames that span it and leave it: translations up
+    to 6 m per scan, rotations up to 0.4 rad per scan (and a few up to 2.5 rad, the half-angle path, at short range), ranges
+    30 ... 250 m, any requested time.  Against the double closed form (numpy) every point obeys the per-point model, the frame
+    bound kmc_b200_frame_accuracy_bound dominates the measured maximum without being loose, and the warning status is raised
+    exactly when the bound at the contract range (120 m) leaves the 1e-5 m contract."""
+    rng = np.random.default_rng(20260)
+    worst_ratio, warned = 0.0, 0
+    for k in range(60):
+        wide = k % 10 == 9
+        max_range = float(rng.choice([30.0, 60.0, 120.0])) if wide else float(rng.choice([30.0, 60.0, 120.0, 200.0, 250.0]))
+        rho = rng.uniform(-1, 1, 3) * rng.choice([0.0, 0.3, 1.5, 3.0, 6.0])
+        axis = rng.standard_normal(3)
+        theta = rng.uniform(1.0, 2.5) if wide else float(rng.choice([0.0, 1e-7, 0.01, 0.06, 0.2, 0.4])) * rng.uniform(0.5, 1.0)
+        xi = np.concatenate([rho, axis / np.linalg.norm(axis) * theta])
+        x_req = float(rng.choice([0.0, 0.5, 1.0, rng.uniform(0, 1)]))
+        pts = helpers.synthetic_scan(20_000, 64, 1000 + k, max_range=max_range)
+        p = capi.frame_params_from_twist(xi, x_req)
+        out = run_frame(cuda, capi, pts, p)
+        ref = helpers.closed_form_deskew(pts, xi, x_req)
+        err = np.abs(out[:, :3].astype(np.float64) - ref)
+        far = np.linalg.norm(pts[:, :3].astype(np.float64), axis=1)
+        delta = np.linalg.norm(ref - pts[:, :3].astype(np.float64), axis=1)
+        per_point = ulp32_half(ref) + (2.5e-7 * delta + 5e-8 * (np.linalg.norm(rho) + theta * far))[:, None]
+        over = float((err - per_point).max())
+        assert over <= 0.0, f"frame {k} (xi={xi}, range {max_range}): a point exceeds the per-point model by {over:.2e} m"
+        bound, _ = capi.frame_accuracy_bound(p, float(far.max()))
+        assert err.max() <= bound, (k, err.max(), bound)
+        worst_ratio = max(worst_ratio, bound / max(err.max(), 2e-6))
+        at_contract, status = capi.frame_accuracy_bound(p, 120.0)
+        assert (status == capi.WARN_ACCURACY) == (at_contract > 1e-5)
+        warned += status == capi.WARN_ACCURACY
+        if status == capi.OK and max_range <= 120.0:
+            assert err.max() < TOL_M, (k, err.max())
+        assert np.array_equal(out[:, 3], pts[:, 3])
+    print(f"60 random frames: frame bound / measured maximum <= {worst_ratio:.2f}; {warned} frames outside the 1e-5 m contract")
+    assert worst_ratio < 6.0 and 0 < warned < 60
+
+
 def test_frame_params_warn_outside_the_accuracy_domain(capi):
     """kmc_b200_frame_params_from_* return the non-fatal KMC_B200_WARN_ACCURACY (constants still valid) when the motion per
     scan puts 1e-5 m out of reach at 120 m; ordinary driving (up to 30 m/s, 1 rad/s) does not warn."""
